@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run once, in the build container (where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+The reference tree is imported read-only with two in-memory shims and no source
+change:
+  * `matplotlib`, `matplotlib.pyplot`, `mpl_toolkits.mplot3d` are stubbed in
+    sys.modules (imported at krige3d.py:17, gslib_reader.py:14);
+  * `np.int = int` (used at super_block.py:138).
+
+Three fixture families are written (all small, all committed):
+
+  c1_reference.npz       the shipped config 1 (testData/test_krige3d.par) run
+                         through Krige3d(par).kt3d() as shipped (SK) and with
+                         ikrige=1 (OK): estimates, variances, neighbour sets,
+                         super-block state.
+  kernels_reference.npz  known-answer vectors for the reference's own jitted
+                         kernels on seeded random inputs: cova3 (all 5 model
+                         types, nested, anisotropic), left_side, right_side,
+                         func_pickup, getindx, SuperBlockSearcher.setup,
+                         Krige3d._set_rotation/_rescaling/_max_covariance.
+  small_*.npz            full Krige3d.kt3d() runs on synthetic cases built so
+                         that the unmodified search is valid (<=1 sample per
+                         super block and fewer than ndmax samples in range;
+                         SURVEY.md section 0, fact 4): SK and OK, nested and
+                         anisotropic variograms, rotated anisotropic search.
+
+Nothing here is imported by the product; the GPU box never needs /root/reference.
+"""
+import io
+import json
+import os
+import sys
+import tempfile
+import types
+import contextlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("K3D_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    sys.dont_write_bytecode = True
+    for name in ("matplotlib", "matplotlib.pyplot", "mpl_toolkits",
+                 "mpl_toolkits.mplot3d"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if not hasattr(np, "int"):
+        np.int = int
+    sys.path.insert(0, REF)
+    import pygeostatistics.krige3d as k3
+    import pygeostatistics.super_block as sb
+    return k3, sb
+
+
+BASE_PAR = {
+    'datafl': 'data.gslib', 'icolx': 0, 'icoly': 1, 'icolz': 2, 'icolvr': 3,
+    'icolsec': 4, 'tmin': -1.0e21, 'tmax': 1.0e21, 'option': 0,
+    'jackfl': 'jackfl.dat', 'jicolx': 0, 'jicoly': 1, 'jicolz': 2,
+    'jicolvr': 3, 'jicolsec': 4, 'idbg': 0, 'dbgfl': 'kt3d.dbg',
+    'outfl': 'out.dat',
+    'nx': 10, 'xmn': 0.5, 'xsiz': 1.0, 'ny': 10, 'ymn': 0.5, 'ysiz': 1.0,
+    'nz': 10, 'zmn': 0.5, 'zsiz': 1.0, 'nxdis': 1, 'nydis': 1, 'nzdis': 1,
+    'ndmin': 1, 'ndmax': 30, 'noct': 0,
+    'radius_hmax': 4.0, 'radius_hmin': 4.0, 'radius_vert': 4.0,
+    'sang1': 0.0, 'sang2': 0.0, 'sang3': 0.0, 'ikrige': 0, 'skmean': 0.0,
+    'idrift': [False] * 9, 'itrend': False, 'secfl': 'secfl.dat',
+    'iseccol': 3, 'nst': 1, 'c0': 0.1, 'it': [1], 'cc': [0.9],
+    'ang1': [0.0], 'ang2': [0.0], 'ang3': [0.0], 'aa_hmax': [8.0],
+    'aa_hmin': [8.0], 'aa_vert': [8.0],
+}
+
+
+def write_gslib(path, cols, names, title="synthetic"):
+    with open(path, "w") as f:
+        f.write(title + "\n%d\n" % len(names))
+        for n in names:
+            f.write(n + "\n")
+        for row in zip(*cols):
+            f.write("\t".join(repr(float(v)) for v in row) + "\n")
+
+
+def run_reference(k3, par, workdir):
+    """Krige3d(par).kt3d() with stdout silenced; returns the object."""
+    pfile = os.path.join(workdir, "case.par")
+    with open(pfile, "w") as f:
+        f.write(json.dumps(par, sort_keys=True, indent=4))
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            k = k3.Krige3d(pfile)
+            k.kt3d()
+    finally:
+        os.chdir(cwd)
+    return k
+
+
+def neighbour_sets(k, nmax):
+    """Per-node neighbour sets in ORIGINAL file index space, ascending, -1 padded."""
+    n = k.nx * k.ny * k.nz
+    out = np.full((n, nmax), -1, dtype=np.int32)
+    cnt = np.zeros(n, dtype=np.int32)
+    nxy = k.nx * k.ny
+    s = k.searcher
+    with contextlib.redirect_stdout(io.StringIO()):
+        for index in range(n):
+            iz = index // nxy
+            iy = (index - iz * nxy) // k.nx
+            ix = index - iz * nxy - iy * k.nx
+            s.search(k.xmn + ix * k.xsiz, k.ymn + iy * k.ysiz,
+                     k.zmn + iz * k.zsiz)
+            ids = np.sort(s.sort_index[np.asarray(s.close_samples, dtype=np.int64)])
+            cnt[index] = s.nclose
+            out[index, :len(ids)] = ids
+    return cnt, out
+
+
+def golden_c1(k3):
+    par = json.load(open(os.path.join(REF, "testData/test_krige3d.par")))
+    par['datafl'] = os.path.join(REF, "testData/test.gslib")
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        ksk = run_reference(k3, dict(par), td)
+        pok = dict(par)
+        pok['ikrige'] = 1
+        kok = run_reference(k3, pok, td)
+        cnt, sets = neighbour_sets(ksk, 32)
+    res['est_sk'] = ksk.estimation
+    res['var_sk'] = ksk.estimation_variance
+    res['est_ok'] = kok.estimation
+    res['var_ok'] = kok.estimation_variance
+    res['nclose'] = cnt
+    res['nbr_sets'] = sets.astype(np.int16)
+    res['sort_index'] = ksk.searcher.sort_index.astype(np.int32)
+    res['nisb'] = np.asarray(ksk.searcher.nisb, dtype=np.int64)
+    res['tmpl'] = np.stack([np.asarray(ksk.searcher.ixsbtosr),
+                            np.asarray(ksk.searcher.iysbtosr),
+                            np.asarray(ksk.searcher.izsbtosr)]).astype(np.int32)
+    res['rotmat'] = ksk.rotmat
+    res['scalars'] = np.array([ksk.maxcov, ksk.resc, ksk.radsqd,
+                               ksk.searcher.nxsup, ksk.searcher.nysup,
+                               ksk.searcher.nzsup, ksk.searcher.xsizsup,
+                               ksk.searcher.ysizsup, ksk.searcher.zsizsup])
+    np.savez_compressed(os.path.join(HERE, "c1_reference.npz"), **res)
+    print("c1: SK est mean %.13f var mean %.15f | OK est mean %.13f var mean %.15f"
+          % (np.mean(res['est_sk']), np.mean(res['var_sk']),
+             np.mean(res['est_ok']), np.mean(res['var_ok'])))
+    print("c1: nclose min/mean/max", cnt.min(), cnt.mean(), cnt.max(),
+          "template", res['tmpl'].shape[1])
+
+
+def golden_kernels(k3, sb):
+    rng = np.random.default_rng(20261019)
+    out = {}
+    # --- rotation matrices / rescale / maxcov through the class methods -----
+    par = dict(BASE_PAR)
+    par.update(nst=4, c0=0.07, it=[1, 2, 3, 5], cc=[0.3, 0.25, 0.2, 0.18],
+               ang1=[30.0, -20.0, 300.0, 0.0], ang2=[10.0, -5.0, 0.0, 45.0],
+               ang3=[0.0, 15.0, -30.0, 5.0], aa_hmax=[9.0, 12.0, 7.0, 5.0],
+               aa_hmin=[4.5, 12.0, 3.0, 2.0], aa_vert=[2.0, 6.0, 7.0, 1.0],
+               radius_hmax=5.0, radius_hmin=3.0, radius_vert=2.0,
+               sang1=40.0, sang2=-10.0, sang3=20.0)
+    with tempfile.TemporaryDirectory() as td:
+        x, y, z = rng.uniform(0, 10, (3, 40))
+        write_gslib(os.path.join(td, "data.gslib"), [x, y, z, rng.normal(size=40)],
+                    ["x", "y", "z", "v"])
+        pfile = os.path.join(td, "case.par")
+        json.dump(par, open(pfile, "w"))
+        cwd = os.getcwd()
+        os.chdir(td)
+        try:
+            k = k3.Krige3d(pfile)
+        finally:
+            os.chdir(cwd)
+    k._preprocess(); k._set_rotation(); k._max_covariance(); k._rescaling()
+    out['rot_par'] = np.array([json.dumps(par)])
+    out['rot_rotmat'] = k.rotmat.copy()
+    out['rot_scalars'] = np.array([k.maxcov, k.resc, k.radsqd])
+    rotmat = k.rotmat.copy()
+    maxcov = k.maxcov
+
+    # --- cova3: 4 nested structures above + a power-model set ---------------
+    npair = 400
+    p1 = rng.uniform(-6, 6, (npair, 3))
+    p2 = rng.uniform(-6, 6, (npair, 3))
+    p2[:10] = p1[:10]                       # coincident -> maxcov
+    p2[10:20] = p1[10:20] + 1e-9            # h^2 < eps boundary
+    it = [1, 2, 3, 5]; cc = [0.3, 0.25, 0.2, 0.18]; aa = [9.0, 12.0, 7.0, 5.0]
+    cov = np.array([k3.cova3(tuple(a), tuple(b), rotmat, maxcov, 4, it, cc, aa)
+                    for a, b in zip(p1, p2)])
+    out['cova_p1'] = p1; out['cova_p2'] = p2; out['cova_out'] = cov
+    itp = [4, 1]; ccp = [0.5, 0.4]; aap = [1.5, 6.0]
+    maxcovp = 0.1 + 999 + 0.4
+    covp = np.array([k3.cova3(tuple(a), tuple(b), rotmat[[0, 1, 4]], maxcovp, 2,
+                              itp, ccp, aap) for a, b in zip(p1, p2)])
+    out['cova_pow_out'] = covp
+    # --- left_side / right_side -------------------------------------------
+    na = 12
+    xa, ya, za = rng.uniform(-5, 5, (3, na))
+    out['ls_xyz'] = np.stack([xa, ya, za])
+    out['ls_sk'] = k3.left_side(xa, ya, za, na, maxcov, rotmat, maxcov, 4, it, cc, aa)
+    out['ls_ok'] = k3.left_side(xa, ya, za, na + 1, maxcov, rotmat, maxcov, 4, it, cc, aa)
+    xdb1 = np.zeros(1)
+    out['rs_point'] = k3.right_side(xa, ya, za, xdb1, xdb1, xdb1, na + 1, maxcov,
+                                    rotmat, maxcov, 4, it, cc, aa, 0.07)
+    # block discretisation, tensor product (repair D9 feeds right_side a joint list)
+    gx, gy, gz = np.meshgrid((np.arange(3) - 1) / 3.0, (np.arange(2) - 0.5) / 2.0,
+                             (np.arange(2) - 0.5) / 2.0, indexing='ij')
+    xdb, ydb, zdb = gx.ravel(), gy.ravel(), gz.ravel()
+    xa2 = xa.copy(); ya2 = ya.copy(); za2 = za.copy()
+    xa2[0], ya2[0], za2[0] = xdb[3], ydb[3], zdb[3]   # coincides with a block point
+    out['rs_block_xyz'] = np.stack([xa2, ya2, za2])
+    out['rs_block_db'] = np.stack([xdb, ydb, zdb])
+    out['rs_block'] = k3.right_side(xa2, ya2, za2, xdb, ydb, zdb, na + 1, maxcov,
+                                    rotmat, maxcov, 4, it, cc, aa, 0.07)
+    # --- func_pickup for rotated anisotropic search -------------------------
+    tm = sb.func_pickup(7, 6, 5, 1.4, 1.7, 2.0, rotmat[-1], 25.0,
+                        np.finfo('float').max)
+    out['pick_args'] = np.array([7, 6, 5, 1.4, 1.7, 2.0, 25.0])
+    out['pick_tmpl'] = np.stack([np.asarray(tm[1]), np.asarray(tm[2]),
+                                 np.asarray(tm[3])]).astype(np.int32)
+    # --- getindx (Numba arange flavour) and setup (numpy flavour) ----------
+    geo = dict(nx=37, xmn=0.35, xsiz=0.7, ny=23, ymn=-3.0, ysiz=1.3, nz=11,
+               zmn=10.05, zsiz=0.1)
+    s = sb.SuperBlockSearcher()
+    for key, v in geo.items():
+        setattr(s, key, v)
+    s.MAXSB = (18, 11, 5)
+    nd = 300
+    x = rng.uniform(0.0, 37 * 0.7, nd); y = rng.uniform(-3.65, -3.65 + 23 * 1.3, nd)
+    z = rng.uniform(10.0, 10.0 + 11 * 0.1, nd)
+    # a few samples exactly on super-block edges (searchsorted side='left')
+    x[:5] = np.arange(1, 6) * (37 * 0.7 / 18)
+    vr = np.core.records.fromarrays(np.stack([x, y, z, rng.normal(size=nd)]),
+                                    names='x,y,z,v', formats='f8,f8,f8,f8')
+    s.vr = vr
+    s.setup()
+    out['setup_geo'] = np.array([json.dumps(geo)])
+    out['setup_xyz'] = np.stack([x, y, z])
+    out['setup_nisb'] = np.asarray(s.nisb, dtype=np.int64)
+    # argsort at super_block.py:135 is unstable: store the block id per sample
+    # (order-independent) rather than the permutation itself.
+    blk = np.empty(nd, dtype=np.int64)
+    bounds = np.concatenate([[0], out['setup_nisb']])
+    for b in range(len(bounds) - 1):
+        blk[s.sort_index[bounds[b]:bounds[b + 1]]] = b
+    out['setup_block_of_sample'] = blk
+    out['setup_sup'] = np.array([s.nxsup, s.nysup, s.nzsup, s.xsizsup, s.ysizsup,
+                                 s.zsizsup, s.xmnsup, s.ymnsup, s.zmnsup])
+    nodes = []
+    for ix in range(37):
+        r = sb.getindx(0.35 + ix * 0.7, -3.0, 10.05, s.xmnsup, s.xsizsup, s.nxsup,
+                       s.ymnsup, s.ysizsup, s.nysup, s.zmnsup, s.zsizsup, s.nzsup)
+        nodes.append(r[0])
+    out['getindx_x'] = np.array(nodes, dtype=np.int64)
+    nodes = []
+    for iy in range(23):
+        r = sb.getindx(0.35, -3.0 + iy * 1.3, 10.05, s.xmnsup, s.xsizsup, s.nxsup,
+                       s.ymnsup, s.ysizsup, s.nysup, s.zmnsup, s.zsizsup, s.nzsup)
+        nodes.append(r[1])
+    out['getindx_y'] = np.array(nodes, dtype=np.int64)
+    nodes = []
+    for iz in range(11):
+        r = sb.getindx(0.35, -3.0, 10.05 + iz * 0.1, s.xmnsup, s.xsizsup, s.nxsup,
+                       s.ymnsup, s.ysizsup, s.nysup, s.zmnsup, s.zsizsup, s.nzsup)
+        nodes.append(r[2])
+    out['getindx_z'] = np.array(nodes, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "kernels_reference.npz"), **out)
+    print("kernels: cova3 %d pairs, template %d offsets, nisb[-1]=%d"
+          % (npair, out['pick_tmpl'].shape[1], out['setup_nisb'][-1]))
+
+
+def one_per_superblock_samples(rng, par, frac):
+    """<=1 sample per super block, strictly inside it (so the unmodified search is valid)."""
+    nsx = min(par['nx'], max(1, min(par['nx'] // 2, 50)) if par['nx'] > 1 else 1)
+    nsy = min(par['ny'], max(1, min(par['ny'] // 2, 50)) if par['ny'] > 1 else 1)
+    nsz = min(par['nz'], max(1, min(par['nz'] // 2, 50)) if par['nz'] > 1 else 1)
+    sx = par['nx'] * par['xsiz'] / nsx
+    sy = par['ny'] * par['ysiz'] / nsy
+    sz = par['nz'] * par['zsiz'] / nsz
+    x0 = par['xmn'] - 0.5 * par['xsiz']
+    y0 = par['ymn'] - 0.5 * par['ysiz']
+    z0 = par['zmn'] - 0.5 * par['zsiz']
+    xs, ys, zs = [], [], []
+    for k in range(nsz):
+        for j in range(nsy):
+            for i in range(nsx):
+                if rng.uniform() < frac:
+                    u = rng.uniform(0.05, 0.95, 3)
+                    xs.append(x0 + (i + u[0]) * sx)
+                    ys.append(y0 + (j + u[1]) * sy)
+                    zs.append(z0 + (k + u[2]) * sz)
+    return np.array(xs), np.array(ys), np.array(zs)
+
+
+SMALL_CASES = {
+    # name: par overrides (valid region of the unmodified reference: SK / OK,
+    # point kriging, noct=0, <=1 sample per super block, < ndmax in range)
+    'small_sk_sph': dict(nx=12, ny=10, nz=8, ikrige=0, skmean=0.3,
+                         radius_hmax=3.2, radius_hmin=3.2, radius_vert=3.2,
+                         ndmax=40, frac=0.5),
+    'small_ok_nested_aniso': dict(
+        nx=14, ny=12, nz=6, ikrige=1, nst=2, c0=0.1, it=[2, 1], cc=[0.4, 0.5],
+        ang1=[30.0, 60.0], ang2=[10.0, 0.0], ang3=[0.0, 0.0],
+        aa_hmax=[10.0, 20.0], aa_hmin=[5.0, 12.0], aa_vert=[2.5, 6.0],
+        radius_hmax=4.5, radius_hmin=3.0, radius_vert=2.2, sang1=30.0,
+        sang2=5.0, sang3=-10.0, ndmax=48, frac=0.45, xsiz=1.5, ysiz=0.8,
+        zsiz=1.2, xmn=10.75, ymn=-4.6, zmn=0.6),
+    'small_ok_gauss_hole_2d': dict(
+        nx=20, ny=16, nz=1, ikrige=1, nst=2, c0=0.2, it=[3, 5], cc=[0.5, 0.3],
+        ang1=[0.0, 45.0], ang2=[0.0, 0.0], ang3=[0.0, 0.0],
+        aa_hmax=[6.0, 9.0], aa_hmin=[6.0, 4.0], aa_vert=[6.0, 9.0],
+        radius_hmax=5.0, radius_hmin=5.0, radius_vert=1.0, ndmax=40, frac=0.6,
+        zmn=0.0),
+    'small_sk_power': dict(nx=10, ny=10, nz=6, ikrige=0, skmean=-0.2, nst=1,
+                           c0=0.05, it=[4], cc=[0.3], aa_hmax=[1.3],
+                           aa_hmin=[1.3], aa_vert=[1.3], radius_hmax=3.5,
+                           radius_hmin=3.5, radius_vert=3.5, ndmax=40,
+                           frac=0.5),
+    'small_ok_ndmin': dict(nx=12, ny=12, nz=4, ikrige=1, radius_hmax=2.6,
+                           radius_hmin=2.6, radius_vert=2.6, ndmin=3, ndmax=40,
+                           frac=0.3),
+}
+
+
+def golden_small(k3):
+    for seed, (name, ov) in enumerate(sorted(SMALL_CASES.items())):
+        rng = np.random.default_rng(1000 + seed)
+        ov = dict(ov)
+        frac = ov.pop('frac')
+        par = dict(BASE_PAR)
+        par.update(ov)
+        x, y, z = one_per_superblock_samples(rng, par, frac)
+        v = rng.normal(size=len(x))
+        with tempfile.TemporaryDirectory() as td:
+            names = ["x", "y", "z", "v"] if par['nz'] > 1 else ["x", "y", "v"]
+            cols = [x, y, z, v] if par['nz'] > 1 else [x, y, v]
+            if par['nz'] == 1:
+                z = np.zeros_like(x)
+            write_gslib(os.path.join(td, "data.gslib"), cols, names)
+            k = run_reference(k3, par, td)
+            cnt, sets = neighbour_sets(k, par['ndmax'])
+        assert cnt.max() < par['ndmax'], (name, cnt.max())
+        assert np.all(np.diff(np.concatenate([[0], k.searcher.nisb])) <= 1), name
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            par=np.array([json.dumps(par)]), x=x, y=y, z=z, v=v,
+            est=k.estimation, var=k.estimation_variance, nclose=cnt,
+            nbr_sets=sets.astype(np.int32))
+        print("%s: nd=%d nodes=%d nclose max %d, NaN %d" % (
+            name, len(x), len(k.estimation), cnt.max(),
+            int(np.isnan(k.estimation).sum())))
+
+
+if __name__ == "__main__":
+    import warnings
+    warnings.simplefilter("ignore")
+    k3, sb = import_reference()
+    golden_c1(k3)
+    golden_kernels(k3, sb)
+    golden_small(k3)
