@@ -1,0 +1,8 @@
+"""B200-native krige3d grid estimation (drop-in for pygeostatistics.krige3d.Krige3d)."""
+from .krige3d import Krige3d, slab_ranges, gather_slabs
+from .gslib_io import SpatialData, write_gslib_grid, read_params
+from .super_block import SuperBlockSearcher
+
+__all__ = ["Krige3d", "SpatialData", "SuperBlockSearcher", "write_gslib_grid", "read_params",
+           "slab_ranges", "gather_slabs"]
+__version__ = "0.1.0"

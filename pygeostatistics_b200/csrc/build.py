@@ -1,0 +1,32 @@
+"""Builds libk3d.so (the C-ABI library of include/k3d.h) in-tree with nvcc for sm_100a.
+
+    python pygeostatistics_b200/csrc/build.py [--force] [--verbose]
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = [os.path.join(HERE, "k3d_kernels.cu")]
+HDR = [os.path.join(ROOT, "include", "k3d.h")]
+OUT = os.path.join(HERE, "libk3d.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+         "-I", os.path.join(ROOT, "include"), "--cudart", "shared"]
+
+
+def build(force=False, verbose=False):
+    newest = max(os.path.getmtime(f) for f in SRC + HDR + [os.path.abspath(__file__)])
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
+        return OUT
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,879 @@
+// k3d_kernels.cu -- sm_100a kernels and C ABI for the krige3d grid-estimation path.
+//
+// One fused kernel does, per grid node, what the reference's node loop does
+// (/root/reference/pygeostatistics/krige3d.py:302-403):
+//   1. super-block neighbour search        super_block.py:163-317 (repairs D3-D5)
+//   2. kriging system assembly             krige3d.py:470-583, 748-801, 838-875
+//   3. solve + estimate + variance         krige3d.py:590-614
+//
+// Mapping to the machine (DESIGN.md has the full account):
+//   * one CTA per "tile" = the grid nodes that fall in one super block; all of them
+//     search the same super blocks, so the candidate samples are staged ONCE per CTA
+//     into shared memory as SoA tiles, in ascending sorted-sample order;
+//   * one warp per node: lanes scan the staged candidates with the reference's exact
+//     (FMA-free) anisotropic distance, compact the in-radius ones with ballots, sort
+//     them by (distance, index) with a shared-memory bitonic network, apply the octant
+//     rule with ballot prefix counts and keep the first ndmax;
+//   * the (n+mdt) system is assembled in shared memory in a mirrored packed-triangular
+//     layout, bordered by the right-hand side and the data vector, so that a single
+//     LDL^T elimination sweep (no pivoting: covariance block is SPD, the constraint
+//     Schur complement is definite) leaves the kriging variance and the estimate in
+//     the two border entries -- no triangular solves, no weights materialised.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see build.py).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "k3d.h"
+
+#define K3D_VERSION_STR "pygeostatistics_b200 k3d 0.1 (sm_100a)"
+#define K3D_EPS 2.220446049250313e-16 /* 7./3-4./3-1, krige3d.py:795,853 */
+#define FULL 0xffffffffu
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local K3dLaunchInfo g_launch = {0, 0, 0, 0, 0, 0, 0, 0};
+
+int fail(int code, const char *fmt, const char *detail = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+#define CUDA_TRY(call)                                                         \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess)                                                 \
+            return fail(K3D_ECUDA, #call ": %s", cudaGetErrorString(e_));      \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// kernel configuration (computed on the host, identical formulas on both sides)
+// ---------------------------------------------------------------------------
+struct KCfg {
+    int warps;      // warps per CTA
+    int rtot;       // ndmax + mdt + 2 rows in the bordered system
+    int ntri;       // rtot*(rtot+1)/2 packed entries
+    int ndp;        // ndmax rounded up to a multiple of 4
+    int kcap;       // per-warp candidate list capacity (multiple of 32)
+    int cs;         // staged candidate capacity per CTA
+    int keepmax;    // max entries that survive a prune: noct>0 ? 8*noct : ndmax
+    int sbz0;       // first super-block z index touched by the slab
+    int ntz;        // number of super-block z indices touched by the slab
+    int pw_bytes;   // per-warp shared bytes
+    int smem_bytes; // total dynamic shared bytes
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+// shared memory carve-up (bytes from the dynamic smem base)
+//   [tri LUT u16 x ntri][stage x,y,z f64 x cs][stage idx i32 x cs][chunk i32 x 3*threads]
+//   [per-warp: union{ P f64 x ntri | keys f64 x kcap + slots i32 x kcap },
+//              xa,ya,za,va,ve f64 x ndp, w f64 x rtot]
+__host__ __device__ inline int off_tri(const KCfg &) { return 0; }
+__host__ __device__ inline int off_stage(const KCfg &c) { return align16(c.ntri * 2); }
+__host__ __device__ inline int off_sidx(const KCfg &c) { return off_stage(c) + c.cs * 24; }
+__host__ __device__ inline int off_chunk(const KCfg &c) { return align16(off_sidx(c) + c.cs * 4); }
+__host__ __device__ inline int off_warp(const KCfg &c) { return align16(off_chunk(c) + c.warps * 32 * 12); }
+__host__ __device__ inline int pw_union(const KCfg &c)
+{
+    int a = c.ntri * 8, b = c.kcap * 12;
+    return align16(a > b ? a : b);
+}
+__host__ __device__ inline int pw_bytes(const KCfg &c)
+{
+    return align16(pw_union(c) + (5 * c.ndp + c.rtot) * 8);
+}
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+
+// super_block.py:349-378: the search distance, evaluated exactly as the reference
+// does -- no fused multiply-add, (r0*dx + r1*dy) + r2*dz, squares summed from 0.0.
+__device__ __forceinline__ double sqdist_exact(double dx, double dy, double dz,
+                                               const double *__restrict__ r)
+{
+    double c0 = __dadd_rn(__dadd_rn(__dmul_rn(r[0], dx), __dmul_rn(r[1], dy)), __dmul_rn(r[2], dz));
+    double c1 = __dadd_rn(__dadd_rn(__dmul_rn(r[3], dx), __dmul_rn(r[4], dy)), __dmul_rn(r[5], dz));
+    double c2 = __dadd_rn(__dadd_rn(__dmul_rn(r[6], dx), __dmul_rn(r[7], dy)), __dmul_rn(r[8], dz));
+    double s = __dmul_rn(c0, c0); // 0.0 + c0*c0 is exact
+    s = __dadd_rn(s, __dmul_rn(c1, c1));
+    s = __dadd_rn(s, __dmul_rn(c2, c2));
+    return s;
+}
+
+// krige3d.py:803-836 inside the covariance: contraction allowed (1e-9 tolerance)
+__device__ __forceinline__ double sqdist_fast(double dx, double dy, double dz,
+                                              const double *__restrict__ r)
+{
+    double c0 = r[0] * dx + r[1] * dy + r[2] * dz;
+    double c1 = r[3] * dx + r[4] * dy + r[5] * dz;
+    double c2 = r[6] * dx + r[7] * dy + r[8] * dz;
+    return c0 * c0 + c1 * c1 + c2 * c2;
+}
+
+// krige3d.py:838-875 (cova3).  d = p1 - p2.
+__device__ __forceinline__ double cova3(const K3dParams &P, double dx, double dy, double dz)
+{
+    double hsqd = sqdist_fast(dx, dy, dz, P.rotmat);
+    if (hsqd < K3D_EPS)
+        return P.maxcov;
+    double cova = 0.0;
+#pragma unroll 1
+    for (int ist = 0; ist < P.nst; ist++) {
+        if (ist != 0)
+            hsqd = sqdist_fast(dx, dy, dz, P.rotmat + 9 * ist);
+        double h = sqrt(hsqd);
+        double a = P.aa[ist], c = P.cc[ist];
+        int it = P.it[ist];
+        if (it == 1) {
+            double hr = h / a;
+            if (hr < 1.0)
+                cova += c * (1.0 - hr * (1.5 - 0.5 * hr * hr));
+        } else if (it == 2) {
+            cova += c * exp(-3.0 * h / a);
+        } else if (it == 3) {
+            double hr = h / a;
+            cova += c * exp(-3.0 * hr * hr);
+        } else if (it == 4) {
+            cova += P.maxcov - c * pow(h, a);
+        } else if (it == 5) {
+            cova += c * cos(h / a * 3.141592653589793);
+        }
+    }
+    return cova;
+}
+
+// krige3d.py:770-801 for one sample: covariance to the block (ndb points)
+__device__ __forceinline__ double cov_to_block(const K3dParams &P, double x, double y,
+                                               double z, const double *__restrict__ db)
+{
+    const int ndb = P.ndb;
+    if (ndb <= 1)
+        return cova3(P, x - db[0], y - db[1], z - db[2]);
+    double cb = 0.0;
+    for (int j = 0; j < ndb; j++) {
+        double dx = x - db[j], dy = y - db[ndb + j], dz = z - db[2 * ndb + j];
+        cb += cova3(P, dx, dy, dz);
+        if (dx * dx + dy * dy + dz * dz < K3D_EPS)
+            cb -= P.c0;
+    }
+    return cb / (double)ndb;
+}
+
+__device__ __forceinline__ bool key_less(double ha, int sa, double hb, int sb)
+{
+    // distances are >= +0, so their bit patterns order like integers
+    long long ka = __double_as_longlong(ha), kb = __double_as_longlong(hb);
+    return (ka < kb) || (ka == kb && sa < sb);
+}
+
+// bitonic sort of (keys, slots)[0..n) ascending by (key, slot); n power of two >= 32
+__device__ __forceinline__ void warp_bitonic(double *keys, int *slots, int n, int lane)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (n >> 1); t += 32) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int l = i | j;
+                bool up = (i & k) == 0;
+                double ha = keys[i], hb = keys[l];
+                int sa = slots[i], sb = slots[l];
+                bool lt = key_less(hb, sb, ha, sa); // b < a
+                if (lt == up) {
+                    keys[i] = hb; keys[l] = ha;
+                    slots[i] = sb; slots[l] = sa;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// sgsim.py:945-964 octant classification (repair D5); d = sample - node
+__device__ __forceinline__ int octant_of(double dx, double dy, double dz)
+{
+    int iq;
+    if (dz >= 0.0) {
+        iq = 3;
+        if (dx <= 0.0 && dy > 0.0) iq = 0;
+        if (dx > 0.0 && dy >= 0.0) iq = 1;
+        if (dx < 0.0 && dy <= 0.0) iq = 2;
+    } else {
+        iq = 7;
+        if (dx <= 0.0 && dy > 0.0) iq = 4;
+        if (dx > 0.0 && dy >= 0.0) iq = 5;
+        if (dx < 0.0 && dy <= 0.0) iq = 6;
+    }
+    return iq;
+}
+
+struct NodeCtx {
+    double xloc, yloc, zloc;
+    const double *qx, *qy, *qz; // candidate coordinate arrays addressed by slot
+};
+
+// Sort the K collected candidates and keep what the reference would keep:
+// noct == 0 -> the ndmax nearest; noct > 0 -> per-octant nearest noct, at most 8*noct.
+__device__ __noinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, double *keys,
+                                       int *slots, int K, int lane)
+{
+    if (K > 1) {
+        int n = 32;
+        while (n < K) n <<= 1;
+        for (int t = K + lane; t < n; t += 32) {
+            keys[t] = __longlong_as_double(0x7ff0000000000000LL);
+            slots[t] = 0x7fffffff;
+        }
+        __syncwarp();
+        warp_bitonic(keys, slots, n, lane);
+    }
+    if (P.noct <= 0)
+        return K < P.ndmax ? K : P.ndmax;
+    const unsigned lt = (1u << lane) - 1u;
+    const int nt = 8 * P.noct;
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int kept = 0;
+    for (int base = 0; base < K && kept < nt; base += 32) {
+        int j = base + lane;
+        bool valid = j < K;
+        int slot = valid ? slots[j] : 0;
+        double key = valid ? keys[j] : 0.0;
+        int iq = 8;
+        if (valid)
+            iq = octant_of(nc.qx[slot] - nc.xloc, nc.qy[slot] - nc.yloc, nc.qz[slot] - nc.zloc);
+        int rank = 0;
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            unsigned m = __ballot_sync(FULL, iq == o);
+            if (iq == o) rank = cnt[o] + __popc(m & lt);
+            cnt[o] += __popc(m);
+        }
+        bool keep = valid && rank < P.noct;
+        unsigned km = __ballot_sync(FULL, keep);
+        __syncwarp();
+        if (keep) {
+            int pos = kept + __popc(km & lt);
+            keys[pos] = key;
+            slots[pos] = slot;
+        }
+        kept += __popc(km);
+        __syncwarp();
+    }
+    return kept;
+}
+
+// scan `count` contiguous candidates (slots slot0..slot0+count) and append the
+// in-radius ones to the warp's list; prunes when the list could overflow.
+__device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
+                                               const NodeCtx &nc, int slot0, int count,
+                                               double *keys, int *slots, int K, int lane)
+{
+    const double *rs = P.rotmat + 9 * P.nst;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < count; base += 32) {
+        int c = base + lane;
+        bool in = false;
+        double h = 0.0;
+        if (c < count) {
+            int s = slot0 + c;
+            // point1 = node, point2 = sample (super_block.py:301-305)
+            h = sqdist_exact(__dsub_rn(nc.xloc, nc.qx[s]), __dsub_rn(nc.yloc, nc.qy[s]),
+                             __dsub_rn(nc.zloc, nc.qz[s]), rs);
+            in = !(h > P.radsqd); // reference: `if hsqd > radsqd: continue`
+        }
+        unsigned m = __ballot_sync(FULL, in);
+        if (m == 0u)
+            continue;
+        if (K + 32 > cfg.kcap) {
+            __syncwarp();
+            K = prune_list(P, nc, keys, slots, K, lane);
+        }
+        if (in) {
+            int pos = K + __popc(m & lt);
+            keys[pos] = h;
+            slots[pos] = slot0 + c;
+        }
+        K += __popc(m);
+    }
+    return K;
+}
+
+__device__ __forceinline__ int pk(int r, int c) { return ((r * (r + 1)) >> 1) + c; } // r >= c
+
+// ---------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+k3d_krige_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const K3dOutputs out,
+                 const int iz0, const int iz1, const __grid_constant__ KCfg cfg)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = cfg.warps * 32;
+
+    uint16_t *tri = (uint16_t *)(smem + off_tri(cfg));
+    double *stx = (double *)(smem + off_stage(cfg));
+    double *sty = stx + cfg.cs;
+    double *stz = sty + cfg.cs;
+    int *stidx = (int *)(smem + off_sidx(cfg));
+    int *chunk = (int *)(smem + off_chunk(cfg)); // [3][nthreads]: lo, cnt, off
+    unsigned char *wbase = smem + off_warp(cfg) + warp * pw_bytes(cfg);
+    double *Pm = (double *)wbase;                   // packed bordered system
+    double *keys = (double *)wbase;                 // aliases Pm during the search
+    int *slots = (int *)(wbase + cfg.kcap * 8);
+    double *xa = (double *)(wbase + pw_union(cfg));
+    double *ya = xa + cfg.ndp, *za = ya + cfg.ndp, *va = za + cfg.ndp, *ve = va + cfg.ndp;
+    double *wv = ve + cfg.ndp;
+
+    __shared__ int s_total, s_warpsum[32];
+
+    // ---- tile geometry -----------------------------------------------------
+    int tile = blockIdx.x;
+    const int sbx = tile % P.nxsup;
+    tile /= P.nxsup;
+    const int sby = tile % P.nysup;
+    const int sbz = cfg.sbz0 + tile / P.nysup;
+    const int x0 = in.nodex0[sbx], x1 = in.nodex0[sbx + 1];
+    const int y0 = in.nodey0[sby], y1 = in.nodey0[sby + 1];
+    int z0 = in.nodez0[sbz], z1 = in.nodez0[sbz + 1];
+    z0 = z0 > iz0 ? z0 : iz0;
+    z1 = z1 < iz1 ? z1 : iz1;
+    const int tnx = x1 - x0, tny = y1 - y0, tnz = z1 - z0;
+    const int tnodes = tnx * tny * tnz;
+    if (tnodes <= 0)
+        return;
+
+    // ---- triangular index LUT: e -> (row<<8 | col), row >= col --------------
+    for (int e = tid; e < cfg.ntri; e += nthreads) {
+        int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while (pk(r + 1, 0) <= e) r++;
+        while (pk(r, 0) > e) r--;
+        tri[e] = (uint16_t)((r << 8) | (e - pk(r, 0)));
+    }
+
+    // ---- stage the candidate samples of this tile (ascending sorted index) ---
+    bool staged = true;
+    {
+        int total = 0;
+        for (int r0 = 0; r0 < in.nruns; r0 += nthreads) {
+            int r = r0 + tid;
+            int lo = 0, cnt = 0;
+            if (r < in.nruns) {
+                const int16_t *rn = in.runs + 4 * r;
+                int by = sby + rn[2], bz = sbz + rn[3];
+                if (by >= 0 && by < P.nysup && bz >= 0 && bz < P.nzsup) {
+                    int bx0 = sbx + rn[0], bx1 = sbx + rn[1];
+                    bx0 = bx0 < 0 ? 0 : bx0;
+                    bx1 = bx1 >= P.nxsup ? P.nxsup - 1 : bx1;
+                    if (bx0 <= bx1) {
+                        int b = (bz * P.nysup + by) * P.nxsup;
+                        lo = in.sbstart[b + bx0];
+                        cnt = in.sbstart[b + bx1 + 1] - lo;
+                    }
+                }
+            }
+            // CTA-wide exclusive scan of cnt
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) s_warpsum[warp] = incl;
+            __syncthreads();
+            int woff = 0, ctot = 0;
+            for (int w = 0; w < cfg.warps; w++) {
+                int v = s_warpsum[w];
+                if (w < warp) woff += v;
+                ctot += v;
+            }
+            chunk[tid] = lo;
+            chunk[nthreads + tid] = cnt;
+            chunk[2 * nthreads + tid] = total + woff + incl - cnt;
+            total += ctot;
+            __syncthreads();
+            if (total <= cfg.cs) {
+                int nr = in.nruns - r0;
+                nr = nr < nthreads ? nr : nthreads;
+                for (int q = warp; q < nr; q += cfg.warps) {
+                    int qlo = chunk[q], qcnt = chunk[nthreads + q], qoff = chunk[2 * nthreads + q];
+                    for (int i = lane; i < qcnt; i += 32) {
+                        stx[qoff + i] = in.sx[qlo + i];
+                        sty[qoff + i] = in.sy[qlo + i];
+                        stz[qoff + i] = in.sz[qlo + i];
+                        stidx[qoff + i] = qlo + i;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) s_total = total;
+        __syncthreads();
+        staged = s_total <= cfg.cs;
+    }
+    const int ncand = s_total;
+    const double *db = in.dbxyz;
+    const size_t slab_off = (size_t)iz0 * P.nx * P.ny;
+    const unsigned lt = (1u << lane) - 1u;
+    (void)lt;
+
+    // ---- nodes of the tile, one warp each ------------------------------------
+    for (int t = warp; t < tnodes; t += cfg.warps) {
+        const int lx = t % tnx, ly = (t / tnx) % tny, lz = t / (tnx * tny);
+        const int ix = x0 + lx, iy = y0 + ly, iz = z0 + lz;
+        const size_t node = ((size_t)iz * P.ny + iy) * P.nx + ix;
+        const size_t o = node - slab_off;
+        NodeCtx nc;
+        // krige3d.py:307-309: xmn + ix*xsiz, multiply then add, unfused
+        nc.xloc = __dadd_rn(P.xmn, __dmul_rn((double)ix, P.xsiz));
+        nc.yloc = __dadd_rn(P.ymn, __dmul_rn((double)iy, P.ysiz));
+        nc.zloc = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
+        double est = __longlong_as_double(0x7ff8000000000000LL), var = est;
+        int status = K3D_ST_OK;
+        int na = 0;
+        double extest = 0.0, resce = 0.0, skmean = P.skmean;
+
+        bool live = true;
+        if (P.ktype == 2 || P.ktype == 3) { // krige3d.py:334-344
+            extest = in.extgrid[o];
+            if (extest < P.tmin || extest >= P.tmax) {
+                status = K3D_ST_EXT_TRIMMED;
+                live = false;
+            }
+            resce = P.maxcov / fmax(extest, 0.0001);
+            if (P.ktype == 2) skmean = extest;
+        }
+
+        if (live) {
+            // ---- 1. neighbour search ------------------------------------------
+            int K = 0;
+            int tested = ncand;
+            if (staged) {
+                nc.qx = stx; nc.qy = sty; nc.qz = stz;
+                K = scan_candidates(P, cfg, nc, 0, ncand, keys, slots, K, lane);
+            } else { // tile too dense for the stage: walk the runs in global memory
+                nc.qx = in.sx; nc.qy = in.sy; nc.qz = in.sz;
+                tested = 0;
+                for (int r = 0; r < in.nruns; r++) {
+                    const int16_t *rn = in.runs + 4 * r;
+                    int by = sby + rn[2], bz = sbz + rn[3];
+                    if (by < 0 || by >= P.nysup || bz < 0 || bz >= P.nzsup) continue;
+                    int bx0 = sbx + rn[0], bx1 = sbx + rn[1];
+                    bx0 = bx0 < 0 ? 0 : bx0;
+                    bx1 = bx1 >= P.nxsup ? P.nxsup - 1 : bx1;
+                    if (bx0 > bx1) continue;
+                    int b = (bz * P.nysup + by) * P.nxsup;
+                    int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
+                    K = scan_candidates(P, cfg, nc, lo, hi - lo, keys, slots, K, lane);
+                    tested += hi - lo;
+                }
+            }
+            if (out.ncand && lane == 0) out.ncand[o] = tested;
+            __syncwarp();
+            K = prune_list(P, nc, keys, slots, K, lane);
+            na = K < P.ndmax ? K : P.ndmax; // krige3d.py:356-375
+            __syncwarp();
+
+            // ---- gather the neighbours, coordinates relative to the node ---------
+            for (int i = lane; i < na; i += 32) {
+                int s = slots[i];
+                int g = staged ? stidx[s] : s;
+                xa[i] = nc.qx[s] - nc.xloc; // krige3d.py:369-371
+                ya[i] = nc.qy[s] - nc.yloc;
+                za[i] = nc.qz[s] - nc.zloc;
+                double v = in.sv[g];
+                double e = (P.ktype == 2 || P.ktype == 3) ? in.ssec[g] : 0.0;
+                va[i] = (P.ktype == 0) ? v - skmean : (P.ktype == 2 ? v - e : v);
+                ve[i] = e;
+                if (out.nbr_idx) out.nbr_idx[o * P.ndmax + i] = g;
+            }
+            if (out.nbr_idx)
+                for (int i = na + lane; i < P.ndmax; i += 32) out.nbr_idx[o * P.ndmax + i] = -1;
+            __syncwarp();
+
+            const int mdt = P.mdt;
+            if (na < P.ndmin || na == 0) { // krige3d.py:377, repair D15
+                status = K3D_ST_NOT_ENOUGH_DATA;
+            } else if (na <= mdt) { // krige3d.py:383
+                status = K3D_ST_NOT_ENOUGH_DRIFT;
+            } else if (na == 1) { // krige3d.py:423-468 (mdt == 0 here)
+                double cb = cov_to_block(P, xa[0], ya[0], za[0], db);
+                double s = cb / P.cbb;
+                double v0 = in.sv[staged ? stidx[slots[0]] : slots[0]];
+                est = s * v0 + (1.0 - s) * skmean;
+                var = P.cbb - s * cb;
+            } else {
+                // ---- 2. assemble the bordered system, mirrored packed lower ----------
+                const int N = na + mdt, R = N + 1;
+                // data-data covariances, strict pairs i > j (krige3d.py:748-763)
+                const int npair = (na * (na - 1)) >> 1;
+                for (int e = lane; e < npair; e += 32) {
+                    int rc = tri[e];
+                    int i = (rc >> 8) + 1, j = rc & 255;
+                    double c = cova3(P, xa[j] - xa[i], ya[j] - ya[i], za[j] - za[i]);
+                    Pm[pk(R - j, R - i)] = c;
+                }
+                // right-hand side and data rows (krige3d.py:770-801)
+                for (int i = lane; i < na; i += 32) {
+                    double cb = cov_to_block(P, xa[i], ya[i], za[i], db);
+                    if (P.itrend) cb = 0.0; // repair D10
+                    const int ri = R - i;
+                    Pm[pk(ri, ri)] = P.maxcov; // cova3(p, p)
+                    Pm[pk(ri, 1)] = cb;        // b row
+                    Pm[pk(ri, 0)] = va[i];     // v row
+                    // constraint rows (krige3d.py:764-767, 493-583, repair D6)
+                    if (mdt > 0) {
+                        int q = na;
+                        Pm[pk(ri, R - q)] = P.unbias;
+                        q++;
+                        double x = xa[i], y = ya[i], z = za[i];
+#pragma unroll
+                        for (int l = 0; l < K3D_MAXDRIFT; l++) {
+                            if (P.idrift[l]) {
+                                double f = l == 0 ? x : l == 1 ? y : l == 2 ? z
+                                         : l == 3 ? x * x : l == 4 ? y * y : l == 5 ? z * z
+                                         : l == 6 ? x * y : l == 7 ? x * z : y * z;
+                                Pm[pk(ri, R - q)] = f * P.resc;
+                                q++;
+                            }
+                        }
+                        if (P.ktype == 3) {
+                            Pm[pk(ri, R - q)] = ve[i] * resce;
+                            q++;
+                        }
+                    }
+                }
+                // constraint block (zeros), its right-hand sides, and the border corner
+                if (lane == 0) {
+                    for (int q1 = na; q1 < N; q1++)
+                        for (int q2 = q1; q2 < N; q2++)
+                            Pm[pk(R - q1, R - q2)] = 0.0;
+                    int q = na;
+                    if (mdt > 0) {
+                        Pm[pk(R - q, 1)] = P.unbias; Pm[pk(R - q, 0)] = 0.0; q++;
+                        for (int l = 0; l < K3D_MAXDRIFT; l++)
+                            if (P.idrift[l]) { Pm[pk(R - q, 1)] = P.bv[l]; Pm[pk(R - q, 0)] = 0.0; q++; }
+                        if (P.ktype == 3) { Pm[pk(R - q, 1)] = extest * resce; Pm[pk(R - q, 0)] = 0.0; q++; }
+                    }
+                    Pm[2] = P.cbb; // (b,b): block covariance
+                    Pm[1] = 0.0;   // (v,b): becomes -estimate
+                    Pm[0] = 0.0;   // (v,v): unused
+                }
+                __syncwarp();
+
+                // ---- 3. LDL^T elimination of the N pivots ---------------------------
+                bool singular = false;
+                for (int M = R; M >= 2; M--) {
+                    const int T = (M * (M + 1)) >> 1;
+                    const double d = Pm[T + M];
+                    if (d == 0.0 || !isfinite(d)) { singular = true; break; }
+                    const double inv = 1.0 / d;
+                    for (int j = lane; j < M; j += 32) wv[j] = Pm[T + j] * inv;
+                    __syncwarp();
+                    const double *u = Pm + T;
+                    for (int e = lane; e < T; e += 32) {
+                        int rc = tri[e];
+                        Pm[e] = fma(-wv[rc >> 8], u[rc & 255], Pm[e]);
+                    }
+                    __syncwarp();
+                }
+                if (singular) {
+                    status = K3D_ST_SINGULAR;
+                } else {
+                    var = Pm[2];  // cbb - b' A^-1 b   (krige3d.py:601)
+                    est = -Pm[1]; // v' A^-1 b          (krige3d.py:603-609)
+                    if (P.ktype == 0 || P.ktype == 2) est += skmean; // krige3d.py:611
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            out.est[o] = est;
+            out.var[o] = var;
+            if (out.nbr_cnt) out.nbr_cnt[o] = na;
+            if (out.status) out.status[o] = (uint8_t)status;
+        }
+        if (!live) {
+            if (out.nbr_idx)
+                for (int i = lane; i < P.ndmax; i += 32) out.nbr_idx[o * P.ndmax + i] = -1;
+            if (out.ncand && lane == 0) out.ncand[o] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// template builder (func_pickup, super_block.py:226-265)
+// ---------------------------------------------------------------------------
+struct Rot9 { double r[9]; };
+
+__global__ void k3d_template_kernel(int nxsup, int nysup, int nzsup, double sxs, double sys,
+                                    double szs, const __grid_constant__ Rot9 rot, double radsqd,
+                                    uint8_t *mask)
+{
+    const int nx2 = 2 * nxsup - 1, ny2 = 2 * nysup - 1, nz2 = 2 * nzsup - 1;
+    const long long n = (long long)nx2 * ny2 * nz2;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(g % nz2), j = (int)((g / nz2) % ny2), i = (int)(g / ((long long)nz2 * ny2));
+        double xo = __dmul_rn((double)(i - (nxsup - 1)), sxs);
+        double yo = __dmul_rn((double)(j - (nysup - 1)), sys);
+        double zo = __dmul_rn((double)(k - (nzsup - 1)), szs);
+        double shortest = 1.7976931348623157e308;
+        // (i1-i2)*0.5 takes the values -1, 0, 1: 27 distinct corner differences
+        for (int a = -1; a <= 1; a++)
+            for (int b = -1; b <= 1; b++)
+                for (int c = -1; c <= 1; c++) {
+                    double xd = __dadd_rn(__dmul_rn((double)a, sxs), xo);
+                    double yd = __dadd_rn(__dmul_rn((double)b, sys), yo);
+                    double zd = __dadd_rn(__dmul_rn((double)c, szs), zo);
+                    // point1 = (0,0,0), point2 = (xd,yd,zd): d = 0 - xd
+                    double h = sqdist_exact(__dsub_rn(0.0, xd), __dsub_rn(0.0, yd),
+                                            __dsub_rn(0.0, zd), rot.r);
+                    shortest = h < shortest ? h : shortest;
+                }
+        mask[g] = shortest <= radsqd ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fp64 pipe probe
+// ---------------------------------------------------------------------------
+__global__ void k3d_dfma_probe(double *sink, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+int make_cfg(const K3dParams *p, KCfg *c)
+{
+    c->rtot = p->ndmax + p->mdt + 2;
+    c->ntri = c->rtot * (c->rtot + 1) / 2;
+    c->ndp = (p->ndmax + 3) & ~3;
+    c->keepmax = p->noct > 0 ? 8 * p->noct : p->ndmax;
+    int need = c->keepmax + 32;
+    int kcap = 256;
+    while (kcap < need + 32) kcap += 32;
+    c->kcap = kcap;
+    return 0;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *k3d_version(void) { return K3D_VERSION_STR; }
+const char *k3d_last_error(void) { return g_err; }
+
+int k3d_last_launch(K3dLaunchInfo *info)
+{
+    if (!info) return fail(K3D_EINVAL, "info is NULL");
+    *info = g_launch;
+    return K3D_OK;
+}
+
+static int validate(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
+                    const K3dOutputs *out)
+{
+    if (!p || !in || !out) return fail(K3D_EINVAL, "NULL argument");
+    if (p->nx < 1 || p->ny < 1 || p->nz < 1) return fail(K3D_EINVAL, "empty grid");
+    if (iz0 < 0 || iz1 > p->nz || iz0 > iz1) return fail(K3D_EINVAL, "bad slab [iz0, iz1)");
+    if (p->ndmax < 1 || p->ndmax > K3D_MAXNDMAX) return fail(K3D_EINVAL, "ndmax outside 1..K3D_MAXNDMAX");
+    if (p->nst < 1 || p->nst > K3D_MAXNST) return fail(K3D_EINVAL, "nst outside 1..K3D_MAXNST");
+    if (p->ndb < 1 || p->ndb > K3D_MAXDIS) return fail(K3D_EINVAL, "ndb outside 1..K3D_MAXDIS");
+    if (p->ktype < 0 || p->ktype > 3) return fail(K3D_EINVAL, "ikrige outside 0..3");
+    if (p->noct < 0 || 8 * p->noct > 512) return fail(K3D_EINVAL, "noct outside 0..64");
+    for (int i = 0; i < p->nst; i++)
+        if (p->it[i] < 1 || p->it[i] > 5) return fail(K3D_EINVAL, "variogram type outside 1..5");
+    if (p->mdt < 0 || p->mdt > K3D_MAXDRIFT + 2) return fail(K3D_EINVAL, "bad mdt");
+    if (!in->sx || !in->sy || !in->sz || !in->sv || !in->sbstart || !in->runs ||
+        !in->nodex0 || !in->nodey0 || !in->nodez0 || !in->dbxyz)
+        return fail(K3D_EINVAL, "NULL input array");
+    if ((p->ktype == 2 || p->ktype == 3) && (!in->ssec || !in->extgrid))
+        return fail(K3D_EINVAL, "ikrige 2/3 needs ssec and extgrid");
+    if (!out->est || !out->var) return fail(K3D_EINVAL, "NULL output array");
+    if ((int64_t)p->nxsup * p->nysup * p->nzsup > 0x7fffffff || in->nd > 0x7fffffff)
+        return fail(K3D_EINVAL, "too many super blocks / samples for int32 indexing");
+    return K3D_OK;
+}
+
+int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
+                   const K3dOutputs *out, void *stream)
+{
+    int rc = validate(p, in, iz0, iz1, out);
+    if (rc) return rc;
+    if (iz0 == iz1) return K3D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KCfg c;
+    memset(&c, 0, sizeof(c));
+    make_cfg(p, &c);
+    // one CTA per super block; CTAs whose super block does not meet the slab exit at once
+    c.sbz0 = 0;
+    c.ntz = p->nzsup;
+    int dev = 0, smem_max = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // 8 warps per CTA, two CTAs per SM: each CTA may use half of the SM's shared memory
+    c.warps = 8;
+    int budget = (smem_max + 1024) / 2 - 1024 - 256;
+    c.cs = 64;
+    int fixed = off_warp(c) - c.cs * 28 + c.warps * pw_bytes(c);
+    int cs = (budget - fixed - 64) / 28;
+    if (cs < 64) { // too big for two CTAs per SM: take the whole SM
+        budget = smem_max - 256;
+        cs = (budget - fixed - 64) / 28;
+        if (cs < 64) return fail(K3D_ECAPACITY, "ndmax/drift configuration exceeds shared memory");
+    }
+    if (cs > 4096) cs = 4096;
+    c.cs = cs & ~31;
+    c.pw_bytes = pw_bytes(c);
+    c.smem_bytes = off_warp(c) + c.warps * c.pw_bytes;
+    if (c.smem_bytes > smem_max) return fail(K3D_ECAPACITY, "shared memory budget exceeded");
+    CUDA_TRY(cudaFuncSetAttribute(k3d_krige_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  c.smem_bytes));
+    long long ntiles = (long long)p->nxsup * p->nysup * c.ntz;
+    if (ntiles > 0x7fffffffLL) return fail(K3D_EINVAL, "too many tiles");
+    k3d_krige_kernel<<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(*p, *in, *out, iz0, iz1, c);
+    CUDA_TRY(cudaGetLastError());
+    g_launch.grid = (int)ntiles;
+    g_launch.block = c.warps * 32;
+    g_launch.smem_bytes = c.smem_bytes;
+    g_launch.warps_per_cta = c.warps;
+    g_launch.stage_capacity = c.cs;
+    g_launch.list_capacity = c.kcap;
+    g_launch.launches += 1;
+    return K3D_OK;
+}
+
+int k3d_build_template(int32_t nxsup, int32_t nysup, int32_t nzsup, double xsizsup,
+                       double ysizsup, double zsizsup, const double *rot9_host, double radsqd,
+                       uint8_t *mask, void *stream)
+{
+    if (!rot9_host || !mask || nxsup < 1 || nysup < 1 || nzsup < 1)
+        return fail(K3D_EINVAL, "bad template arguments");
+    Rot9 r;
+    memcpy(r.r, rot9_host, sizeof(r.r));
+    long long n = (long long)(2 * nxsup - 1) * (2 * nysup - 1) * (2 * nzsup - 1);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k3d_template_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(nxsup, nysup, nzsup, xsizsup,
+                                                                 ysizsup, zsizsup, r, radsqd, mask);
+    CUDA_TRY(cudaGetLastError());
+    return K3D_OK;
+}
+
+int k3d_measure_fp64_peak(double *tflops, double *ms, void *stream)
+{
+    if (!tflops) return fail(K3D_EINVAL, "tflops is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    double *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 1 << 16, blocks = 148 * 8, threads = 256;
+    k3d_dfma_probe<<<blocks, threads, 0, st>>>(sink, 1024); // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0, st));
+        k3d_dfma_probe<<<blocks, threads, 0, st>>>(sink, iters);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+        if (t < best) best = t;
+    }
+    CUDA_TRY(cudaGetLastError());
+    double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms) *ms = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return K3D_OK;
+}
+
+int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
+                        const K3dOutputs *out)
+{
+    int rc = validate(p, in, iz0, iz1, out);
+    if (rc) return rc;
+    const size_t nd = (size_t)in->nd;
+    const size_t nsb = (size_t)p->nxsup * p->nysup * p->nzsup;
+    const size_t nodes = (size_t)(iz1 - iz0) * p->nx * p->ny;
+    const bool ext = (p->ktype == 2 || p->ktype == 3);
+    cudaStream_t st = nullptr;
+    CUDA_TRY(cudaStreamCreate(&st));
+    // one device arena for everything
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    size_t o_sx = take(nd * 8), o_sy = take(nd * 8), o_sz = take(nd * 8), o_sv = take(nd * 8);
+    size_t o_sec = take(ext ? nd * 8 : 0), o_sb = take((nsb + 1) * 4), o_runs = take((size_t)in->nruns * 8);
+    size_t o_nx = take((p->nxsup + 1) * 4), o_ny = take((p->nysup + 1) * 4), o_nz = take((p->nzsup + 1) * 4);
+    size_t o_db = take((size_t)p->ndb * 24), o_ext = take(ext ? nodes * 8 : 0);
+    size_t o_est = take(nodes * 8), o_var = take(nodes * 8);
+    size_t o_ni = take(out->nbr_idx ? nodes * p->ndmax * 4 : 0), o_nc = take(out->nbr_cnt ? nodes * 4 : 0);
+    size_t o_st = take(out->status ? nodes : 0), o_ca = take(out->ncand ? nodes * 4 : 0);
+    unsigned char *d = nullptr;
+    if (cudaMalloc(&d, off ? off : 256) != cudaSuccess) {
+        cudaStreamDestroy(st);
+        return fail(K3D_ENOMEM, "device allocation failed");
+    }
+    rc = K3D_OK;
+#define H2D(dst, src, bytes)                                                              \
+    if (rc == K3D_OK && (bytes) > 0 &&                                                    \
+        cudaMemcpyAsync(d + (dst), (src), (bytes), cudaMemcpyHostToDevice, st) != cudaSuccess) \
+        rc = fail(K3D_ECUDA, "host to device copy failed");
+    H2D(o_sx, in->sx, nd * 8) H2D(o_sy, in->sy, nd * 8) H2D(o_sz, in->sz, nd * 8) H2D(o_sv, in->sv, nd * 8)
+    if (ext) { H2D(o_sec, in->ssec, nd * 8) H2D(o_ext, in->extgrid, nodes * 8) }
+    H2D(o_sb, in->sbstart, (nsb + 1) * 4) H2D(o_runs, in->runs, (size_t)in->nruns * 8)
+    H2D(o_nx, in->nodex0, (p->nxsup + 1) * 4) H2D(o_ny, in->nodey0, (p->nysup + 1) * 4)
+    H2D(o_nz, in->nodez0, (p->nzsup + 1) * 4) H2D(o_db, in->dbxyz, (size_t)p->ndb * 24)
+#undef H2D
+    if (rc == K3D_OK) {
+        K3dInputs di = *in;
+        di.sx = (double *)(d + o_sx); di.sy = (double *)(d + o_sy); di.sz = (double *)(d + o_sz);
+        di.sv = (double *)(d + o_sv); di.ssec = ext ? (double *)(d + o_sec) : nullptr;
+        di.sbstart = (int32_t *)(d + o_sb); di.runs = (int16_t *)(d + o_runs);
+        di.nodex0 = (int32_t *)(d + o_nx); di.nodey0 = (int32_t *)(d + o_ny); di.nodez0 = (int32_t *)(d + o_nz);
+        di.dbxyz = (double *)(d + o_db); di.extgrid = ext ? (double *)(d + o_ext) : nullptr;
+        K3dOutputs dout;
+        dout.est = (double *)(d + o_est); dout.var = (double *)(d + o_var);
+        dout.nbr_idx = out->nbr_idx ? (int32_t *)(d + o_ni) : nullptr;
+        dout.nbr_cnt = out->nbr_cnt ? (int32_t *)(d + o_nc) : nullptr;
+        dout.status = out->status ? (uint8_t *)(d + o_st) : nullptr;
+        dout.ncand = out->ncand ? (int32_t *)(d + o_ca) : nullptr;
+        rc = k3d_krige_slab(p, &di, iz0, iz1, &dout, st);
+    }
+#define D2H(dst, src, bytes)                                                              \
+    if (rc == K3D_OK && (dst) && (bytes) > 0 &&                                           \
+        cudaMemcpyAsync((dst), d + (src), (bytes), cudaMemcpyDeviceToHost, st) != cudaSuccess) \
+        rc = fail(K3D_ECUDA, "device to host copy failed");
+    D2H(out->est, o_est, nodes * 8) D2H(out->var, o_var, nodes * 8)
+    D2H(out->nbr_idx, o_ni, nodes * p->ndmax * 4) D2H(out->nbr_cnt, o_nc, nodes * 4)
+    D2H(out->status, o_st, nodes) D2H(out->ncand, o_ca, nodes * 4)
+#undef D2H
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == K3D_OK)
+        rc = fail(K3D_ECUDA, "kernel execution failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+} // extern "C"

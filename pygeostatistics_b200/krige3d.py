@@ -1,0 +1,497 @@
+"""Krige3d -- drop-in for the reference's 3-D kriging program on a B200.
+
+Same constructor, parameter files, attributes and driver method as
+/root/reference/pygeostatistics/krige3d.py:27-411:
+
+    k = Krige3d("testData/test_krige3d.par")
+    k.kt3d()                      # or k.kriging()
+    k.estimation, k.estimation_variance
+
+What differs is where the node loop (krige3d.py:302-411) runs: the super-block search,
+the kriging-system assembly and the solve are one fused sm_100a kernel reached through
+the C ABI of include/k3d.h.  There is no CPU fallback.
+
+Beyond the reference (it parses these but crashes on them):
+universal kriging drift terms, kriging with external drift / non-stationary SK (`secfl`),
+octant search (`noct`), block kriging (`nxdis/nydis/nzdis`), `itrend`, and the gslib
+output file (`outfl`, via write_output()).
+"""
+import ctypes as C
+import time
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _native
+from .gslib_io import SpatialData, read_params, read_grid_column, write_gslib_grid
+from .super_block import SuperBlockSearcher
+
+EPS = np.finfo(float).eps
+
+
+def slab_ranges(nz, world_size):
+    """Contiguous z-plane ranges [iz0, iz1), one per rank, sizes differing by at most 1."""
+    base, extra = divmod(nz, world_size)
+    out, z = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append((z, z + n))
+        z += n
+    return out
+
+
+def gather_slabs(local, ranges, plane, group=None):
+    """All-gather per-rank slab arrays (1-D tensors, rank r holding planes ranges[r]) into
+    the full grid on every rank.  Slabs are padded to the largest slab so a single
+    all_gather_into_tensor moves everything (NCCL over NVLink on GPUs, gloo on CPU)."""
+    import torch.distributed as dist
+    world = len(ranges)
+    maxp = max(b - a for a, b in ranges)
+    pad = torch.zeros(maxp * plane, dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local
+    full = torch.empty(world * maxp * plane, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, pad, group=group)
+    parts = [full[r * maxp * plane: r * maxp * plane + (b - a) * plane]
+             for r, (a, b) in enumerate(ranges)]
+    return torch.cat(parts)
+
+
+class _MemoryData(object):
+    """SpatialData look-alike over in-memory columns (same record-array layout)."""
+
+    def __init__(self, columns):
+        names = list(columns.keys())
+        arrays = [np.ascontiguousarray(columns[n], dtype=np.float64) for n in names]
+        self.datafl = None
+        self.property_name = [n for n in names if n not in ('x', 'y', 'z')]
+        self._2d = 'z' not in names
+        if self._2d:
+            names.append('z')
+            arrays.append(np.zeros_like(arrays[0]))
+        self.vr = np.rec.fromarrays(arrays, dtype=np.dtype(
+            {'names': names, 'formats': ['f8'] * len(names)}))
+
+
+class Krige3d(object):
+    """Performing 3d Kriging with super block search (GPU)."""
+
+    def __init__(self, param_file, data=None, secondary=None):
+        """`param_file`: path of a JSON .par file (as in the reference), or the same
+        mapping already parsed.  `data` (optional): ordered mapping column name -> 1-D
+        array used instead of reading `datafl`; `secondary` (optional): the external-drift
+        value of every grid node (x fastest) used instead of reading `secfl`."""
+        self.param_file = param_file
+        self._read_params()
+        self._check_params()
+        self.data = SpatialData(self.datafl) if data is None else _MemoryData(data)
+        self._secondary = secondary
+        self.property_name = self.data.property_name
+        self.vr = self.data.vr
+        self.rotmat = None
+        self.estimation = None
+        self.estimation_variance = None
+        self.status = None
+        self.neighbours = None
+        self.neighbour_count = None
+        self.xdb = self.ydb = self.zdb = None
+        self._2d = self.data._2d
+        self.searcher = None
+        self.const = None
+        self._block_covariance = None
+        self.unbias = None
+        self.maxcov = None
+        self._mdt = None
+        self.resc = None
+        self.verbose = True
+        self.timings = {}
+        self._dev = None
+
+    # ------------------------------------------------------------------ parameters
+    def _read_params(self):
+        params = self.param_file if isinstance(self.param_file, dict) \
+            else read_params(self.param_file)
+        g = params.__getitem__  # KeyError for a missing key, like the reference
+        self.datafl = g('datafl')
+        self.ixl, self.iyl, self.izl = g('icolx'), g('icoly'), g('icolz')
+        self.ivrl, self.iextv = g('icolvr'), g('icolsec')
+        self.tmin, self.tmax = g('tmin'), g('tmax')
+        self.koption = g('option')
+        self.jackfl = g('jackfl')
+        self.ixlj, self.iylj, self.izlj = g('jicolx'), g('jicoly'), g('jicolz')
+        self.ivrlj, self.iextvj = g('jicolvr'), g('jicolsec')
+        self.idbg, self.dbgfl, self.outfl = g('idbg'), g('dbgfl'), g('outfl')
+        self.nx, self.xmn, self.xsiz = g('nx'), g('xmn'), g('xsiz')
+        self.ny, self.ymn, self.ysiz = g('ny'), g('ymn'), g('ysiz')
+        self.nz, self.zmn, self.zsiz = g('nz'), g('zmn'), g('zsiz')
+        self.nxdis, self.nydis, self.nzdis = g('nxdis'), g('nydis'), g('nzdis')
+        self.ndmin, self.ndmax, self.noct = g('ndmin'), g('ndmax'), g('noct')
+        self.radius_hmax, self.radius_hmin = g('radius_hmax'), g('radius_hmin')
+        self.radius_vert = g('radius_vert')
+        self.sang1, self.sang2, self.sang3 = g('sang1'), g('sang2'), g('sang3')
+        self.ktype, self.skmean = g('ikrige'), g('skmean')
+        self.idrift, self.itrend = list(g('idrift')), g('itrend')
+        self.extfl, self.iextve = g('secfl'), g('iseccol')
+        self.nst, self.c0 = g('nst'), g('c0')
+        self.it, self.cc = list(g('it')), list(g('cc'))
+        self.ang1, self.ang2, self.ang3 = list(g('ang1')), list(g('ang2')), list(g('ang3'))
+        self.aa_hmax, self.aa_hmin = list(g('aa_hmax')), list(g('aa_hmin'))
+        self.aa_vert = list(g('aa_vert'))
+
+    def _check_params(self):
+        # krige3d.py:132-159 (same messages)
+        if self.radius_hmax <= 0:
+            raise ValueError("radius_hmax should be larger than zero.")
+        if self.nst <= 0:
+            raise ValueError("nst must be at least 1.")
+        for vtype, a_range in zip(self.it, self.aa_hmax):
+            if vtype not in (1, 2, 3, 4, 5):
+                raise ValueError("INVALID variogram number {}".format(vtype))
+            if vtype == 4 and (a_range < 0 or a_range > 2.0):
+                raise ValueError("INVALID power variogram")
+        if self.ktype == 3 and self.iextv <= 0:
+            raise ValueError("Must have exteranl variable")
+        if self.ixl < 0 and self.nx > 1:
+            raise ValueError("WARNING: ixl=0 and nx>1 !")
+        if self.iyl < 0 and self.ny > 1:
+            raise ValueError("WARNING: iyl=0 and ny>1 !")
+        if self.izl < 0 and self.nz > 1:
+            raise ValueError("WARNING: izl=0 and nz>1 !")
+        for item in self.idrift:
+            if not isinstance(item, bool):
+                raise ValueError("Invalid drift term {}".format(item))
+        # limits of this build (include/k3d.h)
+        if self.nst > _native.MAXNST:
+            raise ValueError("nst > {} is not supported".format(_native.MAXNST))
+        if not 1 <= self.ndmax <= _native.MAXNDMAX:
+            raise ValueError("ndmax must be in 1..{}".format(_native.MAXNDMAX))
+        if self.koption != 0:
+            raise NotImplementedError("cross-validation / jackknife (option 1, 2) is not "
+                                      "implemented (it crashes in the reference as well)")
+
+    def read_data(self):
+        """(Re)load `datafl`.  The reference does this in the constructor."""
+        self.data = SpatialData(self.datafl)
+        self.property_name = self.data.property_name
+        self.vr = self.data.vr
+        self._2d = self.data._2d
+
+    # ------------------------------------------------------------------ once-per-run set-up
+    def _preprocess(self):
+        const = namedtuple('Krige3d_const', ['PMX', 'MAXNST', 'MAXDT', 'MAXSB', 'MAXDIS',
+                                             'MAXSAM', 'UNEST'])
+
+        def maxsb(n):
+            return min(int(n / 2), 50) if n > 1 else 1
+
+        self.const = const(PMX=999, MAXNST=4, MAXDT=9,
+                           MAXSB=(maxsb(self.nx), maxsb(self.ny), maxsb(self.nz)),
+                           MAXDIS=self.nxdis * self.nydis * self.nzdis,
+                           MAXSAM=self.ndmax + 1, UNEST=np.nan)
+        self.radsqd = self.radius_hmax * self.radius_hmax
+        self.sanis1 = self.radius_hmin / self.radius_hmax
+        self.sanis2 = self.radius_vert / self.radius_hmax
+        self.anis1 = np.array(self.aa_hmin) / np.maximum(self.aa_hmax, EPS)
+        self.anis2 = np.array(self.aa_vert) / np.maximum(self.aa_hmax, EPS)
+
+    def _set_rotation(self):
+        """rotmat[(nst+1),3,3]; the last matrix is the search ellipsoid (krige3d.py:211-253).
+        The azimuth test `ang <= 0 and ang < 270` is the reference's, kept so that the
+        matrices -- and hence every search distance -- are bit-identical."""
+        ang1 = np.append(self.ang1, self.sang1)
+        ang2 = np.append(self.ang2, self.sang2)
+        ang3 = np.append(self.ang3, self.sang3)
+        anis1 = np.append(self.anis1, self.sanis1)
+        anis2 = np.append(self.anis2, self.sanis2)
+        alpha = np.array([np.deg2rad(90 - a) if (a <= 0 and a < 270) else np.deg2rad(450 - a)
+                          for a in ang1])
+        beta, theta = np.deg2rad(-ang2), np.deg2rad(ang3)
+        sina, sinb, sint = np.sin(alpha), np.sin(beta), np.sin(theta)
+        cosa, cosb, cost = np.cos(alpha), np.cos(beta), np.cos(theta)
+        afac1 = 1.0 / np.maximum(anis1, EPS)
+        afac2 = 1.0 / np.maximum(anis2, EPS)
+        rot = np.full((ang1.shape[0], 3, 3), np.nan)
+        rot[:, 0, 0] = cosb * cosa
+        rot[:, 0, 1] = cosb * sina
+        rot[:, 0, 2] = -sinb
+        rot[:, 1, 0] = afac1 * (-cost * sina + sint * sinb * cosa)
+        rot[:, 1, 1] = afac1 * (cost * cosa + sint * sinb * sina)
+        rot[:, 1, 2] = afac1 * (sint * cosb)
+        rot[:, 2, 0] = afac2 * (sint * sina + cost * sinb * cosa)
+        rot[:, 2, 1] = afac2 * (-sint * cosa + cost * sinb * sina)
+        rot[:, 2, 2] = afac2 * (cost * cosb)
+        self.rotmat = rot
+
+    def _max_covariance(self):
+        self.maxcov = self.c0
+        for ist in range(self.nst):
+            self.maxcov += self.const.PMX if self.it[ist] == 4 else self.cc[ist]
+
+    def _rescaling(self):
+        if self.radsqd < 1:
+            self.resc = 2 * self.radius_hmax / max(self.maxcov, 0.0001)
+        else:
+            self.resc = (4 * self.radsqd) / max(self.maxcov, 0.0001)
+        if self.resc <= 0:
+            raise ValueError("rescaling value is wrong, {}".format(self.resc))
+        self.resc = 1 / self.resc
+
+    @property
+    def mdt(self):
+        """Number of constraint rows (krige3d.py:636-662)."""
+        if self._mdt is None:
+            if self.ktype == 0 or self.ktype == 2:
+                self.idrift = [False] * 9
+                self._mdt = 0
+            else:
+                self._mdt = 1 + sum(1 for b in self.idrift if b) + (1 if self.ktype == 3 else 0)
+        return self._mdt
+
+    def _create_searcher(self):
+        s = SuperBlockSearcher()
+        s.nx, s.xmn, s.xsiz = self.nx, self.xmn, self.xsiz
+        s.ny, s.ymn, s.ysiz = self.ny, self.ymn, self.ysiz
+        s.nz, s.zmn, s.zsiz = self.nz, self.zmn, self.zsiz
+        s.vr = self.vr
+        s.MAXSB = self.const.MAXSB
+        s.rotmat = self.rotmat[-1]
+        s.radsqd = self.radsqd
+        s.noct = self.noct
+        s.setup()
+        s.pickup(self._device())
+        self.searcher = s
+        self.vr = s.vr  # sorted by super block (krige3d.py:690)
+
+    def _block_discretization(self):
+        """ndb discretisation points of a block, offsets from its centre
+        (krige3d.py:692-707; the three axes are combined as a tensor product, x outer)."""
+        self.nxdis = max(1, self.nxdis)
+        self.nydis = max(1, self.nydis)
+        self.nzdis = max(1, self.nzdis)
+        self.ndb = self.nxdis * self.nydis * self.nzdis
+        if self.ndb > _native.MAXDIS:
+            raise ValueError("Too many discretization points")
+        xdis, ydis, zdis = self.xsiz / self.nxdis, self.ysiz / self.nydis, self.zsiz / self.nzdis
+        ax = np.arange(0, self.nxdis, 1) * xdis + (-0.5 * self.xsiz + 0.5 * xdis)
+        ay = np.arange(0, self.nydis, 1) * ydis + (-0.5 * self.ysiz + 0.5 * ydis)
+        az = np.arange(0, self.nzdis, 1) * zdis + (-0.5 * self.zsiz + 0.5 * zdis)
+        gx, gy, gz = np.meshgrid(ax, ay, az, indexing='ij')
+        self.xdb, self.ydb, self.zdb = gx.ravel(), gy.ravel(), gz.ravel()
+
+    def _cova3_host(self, p1, p2):
+        """cova3 (krige3d.py:838-875) in numpy -- only for the once-per-run block covariance."""
+        d = np.asarray(p1, float) - np.asarray(p2, float)
+
+        def sq(r):
+            c = r @ d
+            return float(c @ c)
+        hsqd = sq(self.rotmat[0])
+        if hsqd < EPS:
+            return self.maxcov
+        cova = 0.0
+        for i in range(self.nst):
+            h = np.sqrt(sq(self.rotmat[i]))
+            a, c, t = self.aa_hmax[i], self.cc[i], self.it[i]
+            if t == 1:
+                hr = h / a
+                if hr < 1:
+                    cova += c * (1 - hr * (1.5 - 0.5 * hr * hr))
+            elif t == 2:
+                cova += c * np.exp(-3.0 * h / a)
+            elif t == 3:
+                cova += c * np.exp(-3.0 * (h / a) * (h / a))
+            elif t == 4:
+                cova += self.maxcov - c * (h ** a)
+            elif t == 5:
+                cova += c * np.cos(h / a * np.pi)
+        return cova
+
+    @property
+    def block_covariance(self):
+        """Average covariance within the block (krige3d.py:616-634)."""
+        if self._block_covariance is None:
+            if self.ndb <= 1:
+                self._block_covariance = self.unbias
+            else:
+                pts = np.stack([self.xdb, self.ydb, self.zdb], axis=1)
+                cov = np.array([[self._cova3_host(a, b) for b in pts] for a in pts])
+                cov[np.diag_indices_from(cov)] -= self.c0
+                self._block_covariance = float(np.mean(cov))
+        return self._block_covariance
+
+    # ------------------------------------------------------------------ device plumbing
+    def _device(self):
+        if self._dev is None:
+            if not torch.cuda.is_available():
+                raise _native.K3dError("Krige3d needs a CUDA device (B200); there is no CPU path")
+            self._dev = torch.device("cuda", torch.cuda.current_device())
+        return self._dev
+
+    def _params_struct(self):
+        P = _native.K3dParams()
+        P.nx, P.ny, P.nz = self.nx, self.ny, self.nz
+        P.xmn, P.ymn, P.zmn = self.xmn, self.ymn, self.zmn
+        P.xsiz, P.ysiz, P.zsiz = self.xsiz, self.ysiz, self.zsiz
+        P.ndmin, P.ndmax, P.noct = self.ndmin, self.ndmax, self.noct
+        P.radsqd = self.radsqd
+        P.ktype, P.itrend = self.ktype, int(bool(self.itrend))
+        P.mdt = self.mdt
+        for i in range(9):
+            P.idrift[i] = int(bool(self.idrift[i]))
+        P.skmean, P.tmin, P.tmax = self.skmean, self.tmin, self.tmax
+        P.nst, P.c0 = self.nst, self.c0
+        for i in range(self.nst):
+            P.it[i], P.cc[i], P.aa[i] = int(self.it[i]), self.cc[i], self.aa_hmax[i]
+        for i, v in enumerate(self.rotmat.ravel()):
+            P.rotmat[i] = v
+        P.maxcov, P.resc, P.unbias, P.cbb = self.maxcov, self.resc, self.unbias, \
+            self.block_covariance
+        for i in range(9):
+            P.bv[i] = self.bv[i]
+        s = self.searcher
+        P.nxsup, P.nysup, P.nzsup, P.ndb = s.nxsup, s.nysup, s.nzsup, self.ndb
+        return P
+
+    def _host_inputs(self):
+        """Pinned host copies of everything the kernel reads."""
+        s = self.searcher
+        sec = self.vr[self.property_name[1]] if (self.ktype in (2, 3)) else None
+        host = dict(
+            sx=np.ascontiguousarray(self.vr['x']), sy=np.ascontiguousarray(self.vr['y']),
+            sz=np.ascontiguousarray(self.vr['z']),
+            sv=np.ascontiguousarray(self.vr[self.property_name[0]]),
+            ssec=None if sec is None else np.ascontiguousarray(sec),
+            sbstart=s.sbstart, runs=s.runs.reshape(-1), nodex0=s.nodex0, nodey0=s.nodey0,
+            nodez0=s.nodez0,
+            dbxyz=np.ascontiguousarray(np.concatenate([self.xdb, self.ydb, self.zdb])))
+        return {k: (None if v is None else torch.from_numpy(v).pin_memory())
+                for k, v in host.items()}
+
+    def _upload(self, host, ext_slab):
+        dev = self._device()
+        d = {k: (None if v is None else v.to(dev, non_blocking=True)) for k, v in host.items()}
+        d['extgrid'] = None if ext_slab is None else ext_slab.to(dev, non_blocking=True)
+        return d
+
+    def _launch(self, P, d, iz0, iz1, out):
+        ptr = lambda t: C.c_void_p(None if t is None else t.data_ptr())
+        I = _native.K3dInputs()
+        I.nd = int(d['sx'].numel())
+        I.sx, I.sy, I.sz, I.sv, I.ssec = ptr(d['sx']), ptr(d['sy']), ptr(d['sz']), ptr(d['sv']), \
+            ptr(d['ssec'])
+        I.sbstart, I.nruns, I.runs = ptr(d['sbstart']), int(d['runs'].numel() // 4), ptr(d['runs'])
+        I.nodex0, I.nodey0, I.nodez0 = ptr(d['nodex0']), ptr(d['nodey0']), ptr(d['nodez0'])
+        I.dbxyz, I.extgrid = ptr(d['dbxyz']), ptr(d['extgrid'])
+        O = _native.K3dOutputs()
+        O.est, O.var = ptr(out['est']), ptr(out['var'])
+        O.nbr_idx, O.nbr_cnt, O.status = ptr(out.get('nbr_idx')), ptr(out.get('nbr_cnt')), \
+            ptr(out.get('status'))
+        O.ncand = ptr(out.get('ncand'))
+        stream = torch.cuda.current_stream(self._device()).cuda_stream
+        _native.check(_native.lib().k3d_krige_slab(C.byref(P), C.byref(I), iz0, iz1,
+                                                  C.byref(O), C.c_void_p(stream)))
+
+    def _alloc_outputs(self, nodes, neighbours):
+        dev = self._device()
+        out = dict(est=torch.empty(nodes, dtype=torch.float64, device=dev),
+                   var=torch.empty(nodes, dtype=torch.float64, device=dev),
+                   status=torch.empty(nodes, dtype=torch.uint8, device=dev))
+        if neighbours:
+            out['nbr_idx'] = torch.empty(nodes * self.ndmax, dtype=torch.int32, device=dev)
+            out['nbr_cnt'] = torch.empty(nodes, dtype=torch.int32, device=dev)
+            out['ncand'] = torch.empty(nodes, dtype=torch.int32, device=dev)
+        return out
+
+    def _external_grid(self):
+        if self.ktype not in (2, 3):
+            return None
+        ext = np.ascontiguousarray(self._secondary, dtype=np.float64) \
+            if self._secondary is not None else read_grid_column(self.extfl, self.iextve)
+        if ext.shape[0] != self.nx * self.ny * self.nz:
+            raise ValueError("secfl holds {} values, grid has {} nodes".format(
+                ext.shape[0], self.nx * self.ny * self.nz))
+        return torch.from_numpy(np.array(ext, dtype=np.float64, copy=True))
+
+    # ------------------------------------------------------------------ the driver
+    def prepare(self):
+        """Everything krige3d.py:255-282 does before the node loop."""
+        t0 = time.time()
+        self._preprocess()
+        self._set_rotation()
+        self._max_covariance()
+        self._rescaling()
+        _ = self.mdt
+        if self.verbose:
+            print("Setting up Super Block Search...")
+        self._create_searcher()
+        self._block_discretization()
+        self.unbias = self.maxcov
+        self.bv = np.array([
+            np.mean(self.xdb), np.mean(self.ydb), np.mean(self.zdb),
+            np.mean(self.xdb * self.xdb), np.mean(self.ydb * self.ydb),
+            np.mean(self.zdb * self.zdb), np.mean(self.xdb * self.ydb),
+            np.mean(self.xdb * self.zdb), np.mean(self.ydb * self.zdb)]) * self.resc
+        self.timings['setup_s'] = time.time() - t0
+
+    def kt3d(self, neighbours=False, group=None):
+        """Krige the whole grid.  Results: `estimation`, `estimation_variance` (numpy
+        float64, length nx*ny*nz, x fastest, NaN = unestimated) and `status` (uint8 codes
+        of include/k3d.h).  With neighbours=True also `neighbours` [nodes, ndmax] (original
+        sample row numbers, nearest first, -1 padded) and `neighbour_count`.
+
+        Under an initialised torch.distributed process group the grid is split into
+        z-slabs, one per rank; every rank ends up with the full arrays."""
+        import torch.distributed as dist
+        self.prepare()
+        P = self._params_struct()
+        world, rank = 1, 0
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ranges = slab_ranges(self.nz, world)
+        iz0, iz1 = ranges[rank]
+        plane = self.nx * self.ny
+        nodes = (iz1 - iz0) * plane
+        if self.verbose:
+            print("Start working on the kriging...")
+        t0 = time.time()
+        host = self._host_inputs()
+        ext = self._external_grid()
+        ext_slab = None if ext is None else ext[iz0 * plane: iz1 * plane].pin_memory()
+        d = self._upload(host, ext_slab)
+        out = self._alloc_outputs(nodes, neighbours)
+        if nodes > 0:
+            self._launch(P, d, iz0, iz1, out)
+        if world > 1:
+            out = {k: gather_slabs(v, ranges, plane * (self.ndmax if k == 'nbr_idx' else 1), group)
+                   for k, v in out.items()}
+        res = {k: v.cpu() for k, v in out.items()}
+        torch.cuda.synchronize(self._device())
+        self.timings['krige_s'] = time.time() - t0
+        self.estimation = res['est'].numpy()
+        self.estimation_variance = res['var'].numpy()
+        self.status = res['status'].numpy()
+        if neighbours:
+            idx = res['nbr_idx'].numpy().reshape(-1, self.ndmax).astype(np.int64)
+            self.neighbour_count = res['nbr_cnt'].numpy()
+            self.candidates_tested = res['ncand'].numpy()
+            orig = np.where(idx >= 0, self.searcher.sort_index[np.maximum(idx, 0)], -1)
+            self.neighbours = orig
+            self.neighbours_sorted_space = idx
+        if self.verbose:
+            print("Kriging Finished.")
+
+    kriging = kt3d
+
+    def write_output(self, path=None, unest=None):
+        """Write `outfl`: Estimate and EstimationVariance, x fastest
+        (gslib_help/kt3d_help.md:37-41)."""
+        if self.estimation is None:
+            raise RuntimeError("run kt3d() first")
+        write_gslib_grid(path or self.outfl, self.estimation, self.estimation_variance,
+                         unest=unest)
+
+    def view2d(self):
+        raise NotImplementedError("plotting is outside the scope of the GPU build")
+
+    def view3d(self):
+        pass

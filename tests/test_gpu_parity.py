@@ -1,0 +1,289 @@
+"""GPU parity: the CUDA path (through the C ABI, via Krige3d) against the CPU oracle and the
+committed golden vectors.  Tolerances (BASELINE.json north_star):
+  neighbours  identical ordered lists of sample ids (bit exact)
+  estimate    1e-9 relative (+ 1e-12 * max|data| absolute: estimates can cancel to ~0)
+  variance    1e-9 relative or 1e-12 absolute (variances are ~0 at data-coincident nodes)
+  NaN pattern identical
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import k3d_configs
+from oracle import kt3d_oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+EST_RTOL, VAR_RTOL, VAR_ATOL = 1e-9, 1e-9, 1e-12
+
+
+def gpu_run(par, data, sec, neighbours=True):
+    from pygeostatistics_b200 import Krige3d
+    k = Krige3d(par, data=data, secondary=sec)
+    k.verbose = False
+    k.kt3d(neighbours=neighbours)
+    return k
+
+
+def oracle_run(par, data, sec, node_list=None, threads=8):
+    if data is None:
+        names, cols = orc.read_geoeas(par['datafl'])
+    else:
+        names, cols = list(data.keys()), dict(data)
+        if 'z' not in cols:
+            cols['z'] = np.zeros_like(cols['x'])
+    prop = [n for n in names if n not in ('x', 'y', 'z')]
+    st = orc.prepare(par, cols, prop)
+    return st, orc.run(st, extgrid=sec, node_list=node_list, threads=threads)
+
+
+def compare(k, st, ores, node_list=None, vmax=1.0, check_neighbours=True):
+    est, var, nbr, cnt = ores
+    sel = slice(None) if node_list is None else node_list
+    gest, gvar = k.estimation[sel], k.estimation_variance[sel]
+    assert np.array_equal(st['sort_index'], k.searcher.sort_index)
+    if check_neighbours:
+        assert np.array_equal(k.neighbour_count[sel], cnt)
+        assert np.array_equal(k.neighbours_sorted_space[sel], nbr.astype(np.int64))
+    assert np.array_equal(np.isnan(gest), np.isnan(est))
+    assert np.array_equal(np.isnan(gvar), np.isnan(var))
+    ok = ~np.isnan(est)
+    if ok.any():
+        derr = np.abs(gest[ok] - est[ok])
+        assert np.all(derr <= EST_RTOL * np.abs(est[ok]) + 1e-12 * vmax), \
+            "estimate: max abs err %g" % derr.max()
+        verr = np.abs(gvar[ok] - var[ok])
+        assert np.all((verr <= VAR_RTOL * np.abs(var[ok])) | (verr <= VAR_ATOL)), \
+            "variance: max abs err %g" % verr.max()
+    return int(ok.sum())
+
+
+# ---------------------------------------------------------------- config 1 (shipped)
+@pytest.mark.parametrize("name,tag", [("c1", "sk"), ("c1ok", "ok")])
+def test_config1_against_unmodified_reference_golden(golden_dir, name, tag):
+    par, data, sec = k3d_configs.config(name)
+    k = gpu_run(par, data, sec)
+    g = np.load(os.path.join(golden_dir, "c1_reference.npz"))
+    e, v = g['est_' + tag], g['var_' + tag]
+    assert not np.isnan(k.estimation).any()
+    assert np.max(np.abs(k.estimation - e) / np.abs(e)) < EST_RTOL
+    assert np.max(np.abs(k.estimation_variance - v)) < 1e-11
+    # neighbour SETS of the unmodified reference (it returns them index-ordered, D4)
+    assert np.array_equal(k.neighbour_count, g['nclose'])
+    sets = np.sort(np.where(k.neighbours >= 0, k.neighbours, 1 << 30), axis=1)
+    sets = np.where(sets == 1 << 30, -1, sets)
+    width = g['nbr_sets'].shape[1]
+    full = np.full((sets.shape[0], width), -1, np.int64)
+    full[:, :min(width, sets.shape[1])] = sets[:, :width]
+    assert np.array_equal(full, g['nbr_sets'].astype(np.int64))
+    # and the ordered lists against the oracle
+    st, ores = oracle_run(par, data, sec)
+    compare(k, st, ores, vmax=20.0)
+    # super-block state the reference exposes
+    assert k.searcher.nsbtosr == g['tmpl'].shape[1]
+    assert np.array_equal(np.stack([k.searcher.ixsbtosr, k.searcher.iysbtosr,
+                                    k.searcher.izsbtosr]), g['tmpl'])
+    assert np.array_equal(k.searcher.nisb, g['nisb'])
+    assert np.array_equal(k.rotmat, g['rotmat'])
+
+
+@pytest.mark.parametrize("name", ["small_sk_sph", "small_ok_nested_aniso",
+                                  "small_ok_gauss_hole_2d", "small_sk_power",
+                                  "small_ok_ndmin"])
+def test_small_goldens_from_unmodified_reference(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    par = json.loads(str(g['par'][0]))
+    data = {'x': g['x'], 'y': g['y'], 'z': g['z'], 'v': g['v']}
+    k = gpu_run(par, data, None)
+    assert np.array_equal(np.isnan(k.estimation), np.isnan(g['est']))
+    ok = ~np.isnan(g['est'])
+    scale = max(1.0, np.max(np.abs(g['est'][ok])))
+    assert np.max(np.abs(k.estimation[ok] - g['est'][ok])) < 1e-9 * scale
+    assert np.max(np.abs(k.estimation_variance[ok] - g['var'][ok])) < \
+        1e-9 * max(1.0, np.max(np.abs(g['var'][ok])))
+    assert np.array_equal(k.neighbour_count, g['nclose'])
+
+
+# ---------------------------------------------------------------- scaled synthetic configs
+@pytest.mark.parametrize("name,scale", [("c2", 0.3), ("c3", 0.18), ("c4", 0.18), ("c5", 0.09)])
+def test_scaled_configs_against_oracle(name, scale):
+    par, data, sec = k3d_configs.config(name, scale)
+    k = gpu_run(par, data, sec)
+    st, ores = oracle_run(par, data, sec)
+    n = compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+    assert n > 0.5 * len(k.estimation)
+
+
+# ---------------------------------------------------------------- full size, sampled nodes
+@pytest.mark.parametrize("name", ["c2", "c3", "c4"])
+def test_full_size_sampled_nodes_against_oracle(name):
+    par, data, sec = k3d_configs.config(name, 1.0)
+    k = gpu_run(par, data, sec)
+    nodes = par['nx'] * par['ny'] * par['nz']
+    rng = np.random.default_rng(7)
+    node_list = np.sort(rng.choice(nodes, 6000, replace=False))
+    # always include the grid corners and a face centre (clipped neighbourhoods)
+    node_list[:3] = [0, par['nx'] - 1, nodes - 1]
+    node_list = np.unique(node_list)
+    st, ores = oracle_run(par, data, sec, node_list=node_list)
+    compare(k, st, ores, node_list=node_list, vmax=float(np.max(np.abs(data['v']))))
+    assert np.all(k.status[~np.isnan(k.estimation)] == 0)
+
+
+def test_full_size_linearity_c3():
+    """Size-independent property at the full 256^3: the OK estimate is linear in the data
+    and the variance does not depend on them: est(a*v + b) = a*est(v) + b."""
+    par, data, sec = k3d_configs.config("c3", 1.0)
+    k1 = gpu_run(par, data, sec, neighbours=False)
+    d2 = dict(data)
+    d2['v'] = 2.5 * data['v'] + 7.0
+    k2 = gpu_run(par, d2, sec, neighbours=False)
+    ok = ~np.isnan(k1.estimation)
+    assert ok.mean() > 0.99
+    assert np.allclose(k2.estimation[ok], 2.5 * k1.estimation[ok] + 7.0, rtol=1e-10, atol=1e-10)
+    assert np.array_equal(k1.estimation_variance[ok], k2.estimation_variance[ok])
+
+
+# ---------------------------------------------------------------- edge cases
+def _edge_par(**kw):
+    par = dict(k3d_configs.BASE)
+    par.update(nx=12, ny=10, nz=6, radius_hmax=3.0, radius_hmin=3.0, radius_vert=3.0,
+               aa_hmax=[6.0], aa_hmin=[6.0], aa_vert=[6.0], ndmax=8)
+    par.update(kw)
+    return par
+
+
+def _edge_data(n, seed=11, ext=(12, 10, 6)):
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(0, 1, (n, 3)) * np.array(ext)
+    return {'x': p[:, 0].copy(), 'y': p[:, 1].copy(), 'z': p[:, 2].copy(),
+            'v': rng.normal(size=n)}
+
+
+@pytest.mark.parametrize("kw,n", [
+    (dict(ikrige=0), 1),                       # a single sample: one-sample closed form
+    (dict(ikrige=1), 1),                       # OK with na=1 <= mdt: everything unestimated
+    (dict(ikrige=0, ndmin=3), 25),             # ndmin rejections
+    (dict(ikrige=1, noct=1, ndmax=8), 200),    # octant search, one per octant
+    (dict(ikrige=1, noct=2, ndmax=5), 200),    # octant search truncated by ndmax
+    (dict(ikrige=1, ndmax=64), 300),           # largest ndmax of the build
+    (dict(ikrige=0, radius_hmax=9.0, radius_hmin=9.0, radius_vert=9.0, ndmax=12), 2500),  # list prune
+    (dict(ikrige=1, idrift=[True, True, True] + [False] * 6, ndmax=12), 300),  # linear drift
+    (dict(ikrige=1, itrend=True, idrift=[True] + [False] * 8, ndmax=12), 300),  # trend
+    (dict(ikrige=0, nxdis=2, nydis=2, nzdis=2, ndmax=10), 200),                # block SK
+    (dict(ikrige=0, it=[3], c0=0.3, cc=[0.7]), 150),                           # gaussian
+    (dict(ikrige=1, it=[4], c0=0.1, cc=[0.4], aa_hmax=[1.2], aa_hmin=[1.2], aa_vert=[1.2]), 150),
+    (dict(ikrige=1, it=[5], c0=0.3, cc=[0.7]), 150),                           # hole effect
+    (dict(ikrige=0, nz=1, zmn=0.0, radius_vert=1.0), 60),                      # 2-D grid
+])
+def test_edge_cases_against_oracle(kw, n):
+    par = _edge_par(**kw)
+    ext = (par['nx'], par['ny'], par['nz'] if par['nz'] > 1 else 0)
+    data = _edge_data(n, ext=ext)
+    k = gpu_run(par, data, None)
+    st, ores = oracle_run(par, data, None)
+    compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+
+
+def test_dense_tile_falls_back_to_global_walk():
+    """More candidates in a tile than the shared-memory stage holds."""
+    par = _edge_par(ikrige=1, nx=8, ny=8, nz=4, radius_hmax=6.0, radius_hmin=6.0,
+                    radius_vert=6.0, ndmax=16)
+    data = _edge_data(9000, seed=5, ext=(8, 8, 4))
+    k = gpu_run(par, data, None)
+    st, ores = oracle_run(par, data, None)
+    compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+
+
+def test_ked_and_nonstationary_sk():
+    par, data, sec = k3d_configs.config("c5", 0.06)
+    for ikrige in (3, 2):
+        p = dict(par, ikrige=ikrige, nxdis=1, nydis=1, nzdis=1)
+        k = gpu_run(p, data, sec)
+        st, ores = oracle_run(p, data, sec)
+        compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+    # external values outside [tmin, tmax) are trimmed (krige3d.py:339)
+    p = dict(par, ikrige=3, tmax=float(np.median(sec)))
+    k = gpu_run(p, data, sec)
+    st, ores = oracle_run(p, data, sec)
+    compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+    assert np.isnan(k.estimation).sum() >= (sec >= p['tmax']).sum()
+
+
+def test_exact_interpolation_and_far_field():
+    """Known answers: a node coinciding with a sample returns the datum with ~0 variance;
+    SK beyond the search radius is unestimated; OK weights reproduce a constant field."""
+    par = _edge_par(ikrige=1, ndmax=12)
+    data = _edge_data(150)
+    data['x'][0], data['y'][0], data['z'][0] = 3.5, 4.5, 2.5  # node (3,4,2)
+    k = gpu_run(par, data, None)
+    node = (2 * par['ny'] + 4) * par['nx'] + 3
+    assert abs(k.estimation[node] - data['v'][0]) < 1e-9
+    assert abs(k.estimation_variance[node]) < 1e-9
+    const = dict(data)
+    const['v'] = np.full_like(data['v'], 3.25)
+    k2 = gpu_run(par, const, None)
+    ok = ~np.isnan(k2.estimation)
+    assert np.allclose(k2.estimation[ok], 3.25, rtol=1e-10)
+
+
+def test_file_based_drop_in(tmp_path):
+    """Krige3d(param_file) with on-disk par/gslib/secfl files and the gslib writer."""
+    from pygeostatistics_b200 import Krige3d, SpatialData
+    par, data, sec = k3d_configs.config("c5", 0.05)
+    pfile = k3d_configs.write_files(str(tmp_path), par, data, sec)
+    k = Krige3d(pfile)
+    k.read_data()
+    k.verbose = False
+    k.kriging()
+    # identical to an in-memory run on the values the reader parsed ...
+    parsed = SpatialData(k.datafl).vr
+    k_mem = gpu_run(par, {n: parsed[n] for n in ('x', 'y', 'z', 'v', 'sec')}, sec)
+    assert np.array_equal(k.estimation, k_mem.estimation, equal_nan=True)
+    # ... and to the original columns up to the text round trip (the reference's
+    # pd.read_csv call uses pandas' fast float parser, which is not correctly rounded)
+    k_org = gpu_run(par, data, sec)
+    assert np.allclose(k.estimation, k_org.estimation, rtol=1e-9, atol=1e-12, equal_nan=True)
+    out = str(tmp_path / "out.dat")
+    k.write_output(out, unest=-999.0)
+    lines = open(out).read().split("\n")
+    assert lines[1] == "2" and lines[2] == "Estimate" and lines[3] == "EstimationVariance"
+    vals = np.loadtxt(out, skiprows=4)
+    assert vals.shape == (par['nx'] * par['ny'] * par['nz'], 2)
+    ok = ~np.isnan(k.estimation)
+    assert np.array_equal(vals[ok, 0], k.estimation[ok])
+    assert np.all(vals[~ok] == -999.0)
+
+
+def test_host_buffer_c_abi_entry():
+    """k3d_krige_slab_host: the same path with host pointers (what a ctypes binding from
+    the reference would call), slab by slab."""
+    import ctypes as C
+    from pygeostatistics_b200 import Krige3d, _native
+    par, data, sec = k3d_configs.config("c3", 0.12)
+    k = gpu_run(par, data, sec)
+    P = k._params_struct()
+    s = k.searcher
+    arrs = dict(sx=np.ascontiguousarray(k.vr['x']), sy=np.ascontiguousarray(k.vr['y']),
+                sz=np.ascontiguousarray(k.vr['z']), sv=np.ascontiguousarray(k.vr['v']),
+                sbstart=s.sbstart, runs=np.ascontiguousarray(s.runs.reshape(-1)),
+                nodex0=s.nodex0, nodey0=s.nodey0, nodez0=s.nodez0,
+                dbxyz=np.concatenate([k.xdb, k.ydb, k.zdb]))
+    I = _native.K3dInputs()
+    I.nd = len(arrs['sx'])
+    for name in ('sx', 'sy', 'sz', 'sv', 'sbstart', 'runs', 'nodex0', 'nodey0', 'nodez0', 'dbxyz'):
+        setattr(I, name, arrs[name].ctypes.data)
+    I.nruns = len(s.runs)
+    plane = par['nx'] * par['ny']
+    est = np.empty(plane * par['nz']); var = np.empty_like(est)
+    half = par['nz'] // 2
+    for a, b in ((0, half), (half, par['nz'])):
+        O = _native.K3dOutputs()
+        O.est = est[a * plane:].ctypes.data
+        O.var = var[a * plane:].ctypes.data
+        _native.check(_native.lib().k3d_krige_slab_host(C.byref(P), C.byref(I), a, b, C.byref(O)))
+    assert np.array_equal(est, k.estimation, equal_nan=True)
+    assert np.array_equal(var, k.estimation_variance, equal_nan=True)
