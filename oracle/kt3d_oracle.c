@@ -385,11 +385,11 @@ static void orc_node(const OrcParams *p, int64_t index, int ntmpl, const int32_t
     int na = nclose < p->ndmax ? nclose : p->ndmax; /* krige3d.py:356-375 */
     nused = na;
     int mdt = orc_mdt(p);
-    if (nbr_cnt) {
+    if (nbr_cnt)
         *nbr_cnt = na;
+    if (nbr_idx)
         for (int i = 0; i < na; i++)
             nbr_idx[i] = (int32_t)cand[i].i;
-    }
     if (na < p->ndmin) /* krige3d.py:377 */
         goto done;
     if (na >= 1 && na <= mdt) /* krige3d.py:383 */
