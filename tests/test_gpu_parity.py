@@ -241,7 +241,9 @@ def test_file_based_drop_in(tmp_path):
     k.kriging()
     # identical to an in-memory run on the values the reader parsed ...
     parsed = SpatialData(k.datafl).vr
-    k_mem = gpu_run(par, {n: parsed[n] for n in ('x', 'y', 'z', 'v', 'sec')}, sec)
+    from pygeostatistics_b200.gslib_io import read_grid_column
+    k_mem = gpu_run(par, {n: parsed[n] for n in ('x', 'y', 'z', 'v', 'sec')},
+                    read_grid_column(k.extfl, k.iextve))
     assert np.array_equal(k.estimation, k_mem.estimation, equal_nan=True)
     # ... and to the original columns up to the text round trip (the reference's
     # pd.read_csv call uses pandas' fast float parser, which is not correctly rounded)
