@@ -66,19 +66,35 @@ struct KCfg {
     int ntz;        // number of super-block z indices touched by the slab
     int pw_bytes;   // per-warp shared bytes
     int smem_bytes; // total dynamic shared bytes
+    int nst;        // number of variogram structures
+    int ndb;        // block discretisation points
+    int urow;       // doubles in one pivot-row buffer (register solve) or rtot (generic)
+};
+
+// Variogram structures prepared on the host for the kernel: the rotation matrix of
+// every structure is pre-divided by its range, so that |rs * d|^2 = (h/a)^2 and no
+// division is left in the covariance (power structures keep the unscaled matrix).
+struct KPrep {
+    double rs[K3D_MAXNST][9];
+    double cc[K3D_MAXNST];
+    double aa[K3D_MAXNST];
+    double eps0s;   // K3D_EPS / a0^2: the "zero distance" test in scaled units
+    int it[K3D_MAXNST];
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 // shared memory carve-up (bytes from the dynamic smem base)
 //   [tri LUT u16 x ntri][stage x,y,z f64 x cs][stage idx i32 x cs][chunk i32 x 3*threads]
+//   [block points transformed per structure f64 x 3*nst*ndb]
 //   [per-warp: union{ P f64 x ntri | keys f64 x kcap + slots i32 x kcap },
-//              xa,ya,za,va,ve f64 x ndp, w f64 x rtot]
+//              xa,ya,za,va,ve f64 x ndp, ut f64 x 3*nst*ndp, pivot rows f64 x 2*urow]
 __host__ __device__ inline int off_tri(const KCfg &) { return 0; }
 __host__ __device__ inline int off_stage(const KCfg &c) { return align16(c.ntri * 2); }
 __host__ __device__ inline int off_sidx(const KCfg &c) { return off_stage(c) + c.cs * 24; }
 __host__ __device__ inline int off_chunk(const KCfg &c) { return align16(off_sidx(c) + c.cs * 4); }
-__host__ __device__ inline int off_warp(const KCfg &c) { return align16(off_chunk(c) + c.warps * 32 * 12); }
+__host__ __device__ inline int off_udb(const KCfg &c) { return align16(off_chunk(c) + c.warps * 32 * 12); }
+__host__ __device__ inline int off_warp(const KCfg &c) { return align16(off_udb(c) + 3 * c.nst * c.ndb * 8); }
 __host__ __device__ inline int pw_union(const KCfg &c)
 {
     int a = c.ntri * 8, b = c.kcap * 12;
@@ -86,12 +102,13 @@ __host__ __device__ inline int pw_union(const KCfg &c)
 }
 __host__ __device__ inline int pw_bytes(const KCfg &c)
 {
-    return align16(pw_union(c) + (5 * c.ndp + c.rtot) * 8);
+    return align16(pw_union(c) + (5 * c.ndp + 3 * c.nst * c.ndp + 2 * c.urow) * 8);
 }
 
 // ---------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ int pk(int r, int c) { return ((r * (r + 1)) >> 1) + c; } // r >= c
 
 // super_block.py:349-378: the search distance, evaluated exactly as the reference
 // does -- no fused multiply-add, (r0*dx + r1*dy) + r2*dz, squares summed from 0.0.
@@ -107,63 +124,183 @@ __device__ __forceinline__ double sqdist_exact(double dx, double dy, double dz,
     return s;
 }
 
-// krige3d.py:803-836 inside the covariance: contraction allowed (1e-9 tolerance)
-__device__ __forceinline__ double sqdist_fast(double dx, double dy, double dz,
-                                              const double *__restrict__ r)
+// Covariance (krige3d.py:838-875, cova3) between two points whose coordinates have been
+// pre-multiplied by every structure's scaled rotation matrix: u[(3*s+k)*stride + idx].
+// |u_i - u_j|^2 is (h/a)^2 of structure s (h^2 for a power structure).
+__device__ __forceinline__ double cova_t(const K3dParams &P, const KPrep &Q,
+                                         const double *__restrict__ ua, int sa, int ia,
+                                         const double *__restrict__ ub, int sb, int ib)
 {
-    double c0 = r[0] * dx + r[1] * dy + r[2] * dz;
-    double c1 = r[3] * dx + r[4] * dy + r[5] * dz;
-    double c2 = r[6] * dx + r[7] * dy + r[8] * dz;
-    return c0 * c0 + c1 * c1 + c2 * c2;
-}
-
-// krige3d.py:838-875 (cova3).  d = p1 - p2.
-__device__ __forceinline__ double cova3(const K3dParams &P, double dx, double dy, double dz)
-{
-    double hsqd = sqdist_fast(dx, dy, dz, P.rotmat);
-    if (hsqd < K3D_EPS)
+    double dx = ua[ia] - ub[ib], dy = ua[sa + ia] - ub[sb + ib], dz = ua[2 * sa + ia] - ub[2 * sb + ib];
+    double h2 = dx * dx + dy * dy + dz * dz;
+    if (h2 < Q.eps0s)
         return P.maxcov;
     double cova = 0.0;
 #pragma unroll 1
-    for (int ist = 0; ist < P.nst; ist++) {
-        if (ist != 0)
-            hsqd = sqdist_fast(dx, dy, dz, P.rotmat + 9 * ist);
-        double h = sqrt(hsqd);
-        double a = P.aa[ist], c = P.cc[ist];
-        int it = P.it[ist];
+    for (int s = 0; s < P.nst; s++) {
+        if (s != 0) {
+            const double *pa = ua + 3 * s * sa, *pb = ub + 3 * s * sb;
+            dx = pa[ia] - pb[ib]; dy = pa[sa + ia] - pb[sb + ib]; dz = pa[2 * sa + ia] - pb[2 * sb + ib];
+            h2 = dx * dx + dy * dy + dz * dz;
+        }
+        const double c = Q.cc[s];
+        const int it = Q.it[s];
         if (it == 1) {
-            double hr = h / a;
-            if (hr < 1.0)
-                cova += c * (1.0 - hr * (1.5 - 0.5 * hr * hr));
+            if (h2 < 1.0) {
+                double hr = sqrt(h2);
+                cova += c * (1.0 - hr * (1.5 - 0.5 * h2));
+            }
         } else if (it == 2) {
-            cova += c * exp(-3.0 * h / a);
+            cova += c * exp(-3.0 * sqrt(h2));
         } else if (it == 3) {
-            double hr = h / a;
-            cova += c * exp(-3.0 * hr * hr);
+            cova += c * exp(-3.0 * h2);
         } else if (it == 4) {
-            cova += P.maxcov - c * pow(h, a);
-        } else if (it == 5) {
-            cova += c * cos(h / a * 3.141592653589793);
+            cova += P.maxcov - c * pow(sqrt(h2), Q.aa[s]);
+        } else {
+            cova += c * cos(sqrt(h2) * 3.141592653589793);
         }
     }
     return cova;
 }
 
-// krige3d.py:770-801 for one sample: covariance to the block (ndb points)
-__device__ __forceinline__ double cov_to_block(const K3dParams &P, double x, double y,
-                                               double z, const double *__restrict__ db)
+// u = rs * p for every structure (p relative to the node)
+__device__ __forceinline__ void transform_point(const K3dParams &P, const KPrep &Q, double x,
+                                                double y, double z, double *u, int stride, int idx)
+{
+    for (int s = 0; s < P.nst; s++) {
+        const double *r = Q.rs[s];
+        u[(3 * s + 0) * stride + idx] = r[0] * x + r[1] * y + r[2] * z;
+        u[(3 * s + 1) * stride + idx] = r[3] * x + r[4] * y + r[5] * z;
+        u[(3 * s + 2) * stride + idx] = r[6] * x + r[7] * y + r[8] * z;
+    }
+}
+
+// krige3d.py:770-801 for one sample: covariance to the block (ndb points, udb = their
+// transformed coordinates, db = raw offsets for the coincidence test)
+__device__ __forceinline__ double cov_to_block(const K3dParams &P, const KPrep &Q,
+                                               const double *ut, int ndp, int i, double x,
+                                               double y, double z, const double *udb,
+                                               const double *__restrict__ db)
 {
     const int ndb = P.ndb;
     if (ndb <= 1)
-        return cova3(P, x - db[0], y - db[1], z - db[2]);
+        return cova_t(P, Q, ut, ndp, i, udb, 1, 0);
     double cb = 0.0;
     for (int j = 0; j < ndb; j++) {
+        cb += cova_t(P, Q, ut, ndp, i, udb, ndb, j);
         double dx = x - db[j], dy = y - db[ndb + j], dz = z - db[2 * ndb + j];
-        cb += cova3(P, dx, dy, dz);
         if (dx * dx + dy * dy + dz * dz < K3D_EPS)
             cb -= P.c0;
     }
     return cb / (double)ndb;
+}
+
+// ---------------------------------------------------------------------------
+// Register-resident LDL^T of the bordered system.
+//
+// The (N+2) x (N+2) lower triangle lives in the warp's registers, 2-D cyclic:
+// mirrored row r, column c (c <= r) belongs to lane (r & 3) * 8 + (c & 7), register
+// m[r >> 2][c >> 3].  Pivot row M is broadcast through a double-buffered shared-memory
+// row; every other operand of the rank-1 update is already in the lane's registers, so
+// one pivot costs A + B shared loads for up to A*B fused multiply-adds per lane.
+// Slots that do not exist for a lane (c > r) or rows already eliminated carry
+// don't-care values: they are only ever combined with other don't-care slots.
+// ---------------------------------------------------------------------------
+template <int AMAX> struct RegSolve {
+    static constexpr int BMAX = ((4 * (AMAX - 1) + 3) >> 3) + 1;
+
+    template <int A>
+    static __device__ __forceinline__ void update(double (&m)[AMAX][BMAX], const double *row,
+                                                  int li, int lj, double ninv)
+    {
+        constexpr int B = A > 0 ? ((4 * (A - 1) + 3) >> 3) + 1 : 0;
+        double w[A > 0 ? A : 1], u[B > 0 ? B : 1];
+#pragma unroll
+        for (int a = 0; a < A; a++) w[a] = row[li + 4 * a] * ninv;
+#pragma unroll
+        for (int b = 0; b < B; b++) u[b] = row[lj + 8 * b];
+#pragma unroll
+        for (int a = 0; a < A; a++)
+#pragma unroll
+            for (int b = 0; b < B; b++)
+                if (8 * b <= 4 * a + 3) m[a][b] = fma(w[a], u[b], m[a][b]);
+    }
+
+    template <int AP>
+    static __device__ __forceinline__ void pivot(double (&m)[AMAX][BMAX], int M, int q,
+                                                 double *rowbuf, int urow, int li, int lj,
+                                                 bool top)
+    {
+        double *row = rowbuf + (M & 1) * urow;
+        if (li == q) {
+#pragma unroll
+            for (int b = 0; b < BMAX; b++)
+                if (8 * b <= 4 * AP + 3) row[lj + 8 * b] = m[AP][b];
+        }
+        __syncwarp();
+        const double ninv = -1.0 / row[M];
+        if (top)
+            update<AP + 1>(m, row, li, lj, ninv);
+        else
+            update<AP>(m, row, li, lj, ninv);
+    }
+
+    template <int AP>
+    static __device__ __forceinline__ void block(double (&m)[AMAX][BMAX], int R, double *rowbuf,
+                                                 int urow, int li, int lj)
+    {
+        if constexpr (AP >= 0) {
+            if (4 * AP <= R) { // uniform: does this row block exist in the system?
+#pragma unroll 1
+                for (int q = 3; q >= 1; q--) {
+                    const int M = 4 * AP + q;
+                    if (M <= R && M >= 2) pivot<AP>(m, M, q, rowbuf, urow, li, lj, true);
+                }
+                if (AP > 0) pivot<AP>(m, 4 * AP, 0, rowbuf, urow, li, lj, false);
+            }
+            block<AP - 1>(m, R, rowbuf, urow, li, lj);
+        }
+    }
+
+    // Eliminates pivots M = R .. 2; leaves var = entry (1,1) and est = -entry (1,0).
+    static __device__ __forceinline__ void run(const double *Pm, int R, double *rowbuf, int urow,
+                                               int lane, double &est, double &var)
+    {
+        const int li = lane >> 3, lj = lane & 7;
+        double m[AMAX][BMAX];
+#pragma unroll
+        for (int a = 0; a < AMAX; a++)
+#pragma unroll
+            for (int b = 0; b < BMAX; b++)
+                if (8 * b <= 4 * a + 3) {
+                    int r = li + 4 * a, c = lj + 8 * b;
+                    m[a][b] = (c <= r && r <= R) ? Pm[pk(r, c)] : 0.0;
+                }
+        block<AMAX - 1>(m, R, rowbuf, urow, li, lj);
+        var = __shfl_sync(FULL, m[0][0], 9);   // (r,c) = (1,1): lane 1*8+1
+        est = -__shfl_sync(FULL, m[0][0], 8);  // (r,c) = (1,0): lane 1*8+0
+    }
+};
+
+// Generic fallback for systems too large for the register solver: the same elimination
+// with the packed triangle kept in shared memory (flat, lane-strided rank-1 updates).
+__device__ __forceinline__ void smem_solve(double *Pm, const uint16_t *tri, int R, double *wv,
+                                           int lane, double &est, double &var)
+{
+    for (int M = R; M >= 2; M--) {
+        const int T = (M * (M + 1)) >> 1;
+        const double inv = 1.0 / Pm[T + M];
+        for (int j = lane; j < M; j += 32) wv[j] = Pm[T + j] * inv;
+        __syncwarp();
+        const double *u = Pm + T;
+        for (int e = lane; e < T; e += 32) {
+            int rc = tri[e];
+            Pm[e] = fma(-wv[rc >> 8], u[rc & 255], Pm[e]);
+        }
+        __syncwarp();
+    }
+    var = Pm[2];
+    est = -Pm[1];
 }
 
 __device__ __forceinline__ bool key_less(double ha, int sa, double hb, int sb)
@@ -304,14 +441,15 @@ __device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &c
     return K;
 }
 
-__device__ __forceinline__ int pk(int r, int c) { return ((r * (r + 1)) >> 1) + c; } // r >= c
 
 // ---------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------
+template <int AMAX>
 __global__ void __launch_bounds__(256, 2)
-k3d_krige_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const K3dOutputs out,
-                 const int iz0, const int iz1, const __grid_constant__ KCfg cfg)
+k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
+                 const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
+                 const __grid_constant__ KCfg cfg)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -329,7 +467,9 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const 
     int *slots = (int *)(wbase + cfg.kcap * 8);
     double *xa = (double *)(wbase + pw_union(cfg));
     double *ya = xa + cfg.ndp, *za = ya + cfg.ndp, *va = za + cfg.ndp, *ve = va + cfg.ndp;
-    double *wv = ve + cfg.ndp;
+    double *ut = ve + cfg.ndp;                      // [3*nst][ndp] transformed coordinates
+    double *wv = ut + 3 * cfg.nst * cfg.ndp;        // pivot rows (2 x urow)
+    double *udb = (double *)(smem + off_udb(cfg));  // [3*nst][ndb] transformed block points
 
     __shared__ int s_total, s_warpsum[32];
 
@@ -356,6 +496,11 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const 
         while (pk(r, 0) > e) r--;
         tri[e] = (uint16_t)((r << 8) | (e - pk(r, 0)));
     }
+
+    // ---- block discretisation points in every structure's coordinates -------
+    for (int j = tid; j < P.ndb; j += nthreads)
+        transform_point(P, Q, in.dbxyz[j], in.dbxyz[P.ndb + j], in.dbxyz[2 * P.ndb + j], udb,
+                        P.ndb, j);
 
     // ---- stage the candidate samples of this tile (ascending sorted index) ---
     bool staged = true;
@@ -491,6 +636,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const 
                 double e = (P.ktype == 2 || P.ktype == 3) ? in.ssec[g] : 0.0;
                 va[i] = (P.ktype == 0) ? v - skmean : (P.ktype == 2 ? v - e : v);
                 ve[i] = e;
+                transform_point(P, Q, xa[i], ya[i], za[i], ut, cfg.ndp, i);
                 if (out.nbr_idx) out.nbr_idx[o * P.ndmax + i] = g;
             }
             if (out.nbr_idx)
@@ -503,7 +649,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const 
             } else if (na <= mdt) { // krige3d.py:383
                 status = K3D_ST_NOT_ENOUGH_DRIFT;
             } else if (na == 1) { // krige3d.py:423-468 (mdt == 0 here)
-                double cb = cov_to_block(P, xa[0], ya[0], za[0], db);
+                double cb = cov_to_block(P, Q, ut, cfg.ndp, 0, xa[0], ya[0], za[0], udb, db);
                 double s = cb / P.cbb;
                 double v0 = in.sv[staged ? stidx[slots[0]] : slots[0]];
                 est = s * v0 + (1.0 - s) * skmean;
@@ -516,12 +662,11 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const 
                 for (int e = lane; e < npair; e += 32) {
                     int rc = tri[e];
                     int i = (rc >> 8) + 1, j = rc & 255;
-                    double c = cova3(P, xa[j] - xa[i], ya[j] - ya[i], za[j] - za[i]);
-                    Pm[pk(R - j, R - i)] = c;
+                    Pm[pk(R - j, R - i)] = cova_t(P, Q, ut, cfg.ndp, j, ut, cfg.ndp, i);
                 }
                 // right-hand side and data rows (krige3d.py:770-801)
                 for (int i = lane; i < na; i += 32) {
-                    double cb = cov_to_block(P, xa[i], ya[i], za[i], db);
+                    double cb = cov_to_block(P, Q, ut, cfg.ndp, i, xa[i], ya[i], za[i], udb, db);
                     if (P.itrend) cb = 0.0; // repair D10
                     const int ri = R - i;
                     Pm[pk(ri, ri)] = P.maxcov; // cova3(p, p)
@@ -568,26 +713,15 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const 
                 __syncwarp();
 
                 // ---- 3. LDL^T elimination of the N pivots ---------------------------
-                bool singular = false;
-                for (int M = R; M >= 2; M--) {
-                    const int T = (M * (M + 1)) >> 1;
-                    const double d = Pm[T + M];
-                    if (d == 0.0 || !isfinite(d)) { singular = true; break; }
-                    const double inv = 1.0 / d;
-                    for (int j = lane; j < M; j += 32) wv[j] = Pm[T + j] * inv;
-                    __syncwarp();
-                    const double *u = Pm + T;
-                    for (int e = lane; e < T; e += 32) {
-                        int rc = tri[e];
-                        Pm[e] = fma(-wv[rc >> 8], u[rc & 255], Pm[e]);
-                    }
-                    __syncwarp();
-                }
-                if (singular) {
+                if constexpr (AMAX > 0)
+                    RegSolve<AMAX>::run(Pm, R, wv, cfg.urow, lane, est, var);
+                else
+                    smem_solve(Pm, tri, R, wv, lane, est, var);
+                if (!isfinite(est) || !isfinite(var)) { // zero pivot (krige3d.py:593)
                     status = K3D_ST_SINGULAR;
+                    est = var = __longlong_as_double(0x7ff8000000000000LL);
                 } else {
-                    var = Pm[2];  // cbb - b' A^-1 b   (krige3d.py:601)
-                    est = -Pm[1]; // v' A^-1 b          (krige3d.py:603-609)
+                    // var = cbb - b' A^-1 b (krige3d.py:601); est = v' A^-1 b (:603-609)
                     if (P.ktype == 0 || P.ktype == 2) est += skmean; // krige3d.py:611
                 }
                 __syncwarp();
@@ -668,7 +802,45 @@ int make_cfg(const K3dParams *p, KCfg *c)
     int kcap = 256;
     while (kcap < need + 32) kcap += 32;
     c->kcap = kcap;
+    c->nst = p->nst;
+    c->ndb = p->ndb;
     return 0;
+}
+
+// register-solver size class for a bordered system of `rtot` rows (0 = generic path)
+int amax_for(int rtot)
+{
+    if (rtot <= 20) return 5;
+    if (rtot <= 36) return 9;
+    if (rtot <= 44) return 11;
+    return 0;
+}
+
+void make_prep(const K3dParams *p, KPrep *q)
+{
+    memset(q, 0, sizeof(*q));
+    for (int s = 0; s < p->nst; s++) {
+        const bool power = p->it[s] == 4;
+        const double inva = power ? 1.0 : 1.0 / p->aa[s];
+        for (int k = 0; k < 9; k++) q->rs[s][k] = p->rotmat[9 * s + k] * inva;
+        q->cc[s] = p->cc[s];
+        q->aa[s] = p->aa[s];
+        q->it[s] = p->it[s];
+    }
+    const double a0 = p->it[0] == 4 ? 1.0 : p->aa[0];
+    q->eps0s = K3D_EPS / (a0 * a0);
+}
+
+template <int AMAX>
+int launch_krige(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
+                 int iz0, int iz1, const KCfg &c, long long ntiles, cudaStream_t st)
+{
+    CUDA_TRY(cudaFuncSetAttribute(k3d_krige_kernel<AMAX>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+    k3d_krige_kernel<AMAX><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(*p, *q, *in, *out,
+                                                                                iz0, iz1, c);
+    CUDA_TRY(cudaGetLastError());
+    return K3D_OK;
 }
 
 } // namespace
@@ -731,6 +903,8 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
     CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     // 8 warps per CTA, two CTAs per SM: each CTA may use half of the SM's shared memory
     c.warps = 8;
+    const int amax = amax_for(c.rtot);
+    c.urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c.rtot;
     int budget = (smem_max + 1024) / 2 - 1024 - 256;
     c.cs = 64;
     int fixed = off_warp(c) - c.cs * 28 + c.warps * pw_bytes(c);
@@ -745,12 +919,17 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
     c.pw_bytes = pw_bytes(c);
     c.smem_bytes = off_warp(c) + c.warps * c.pw_bytes;
     if (c.smem_bytes > smem_max) return fail(K3D_ECAPACITY, "shared memory budget exceeded");
-    CUDA_TRY(cudaFuncSetAttribute(k3d_krige_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  c.smem_bytes));
     long long ntiles = (long long)p->nxsup * p->nysup * c.ntz;
     if (ntiles > 0x7fffffffLL) return fail(K3D_EINVAL, "too many tiles");
-    k3d_krige_kernel<<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(*p, *in, *out, iz0, iz1, c);
-    CUDA_TRY(cudaGetLastError());
+    KPrep q;
+    make_prep(p, &q);
+    switch (amax) {
+    case 5: rc = launch_krige<5>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
+    case 9: rc = launch_krige<9>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
+    case 11: rc = launch_krige<11>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
+    default: rc = launch_krige<0>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
+    }
+    if (rc) return rc;
     g_launch.grid = (int)ntiles;
     g_launch.block = c.warps * 32;
     g_launch.smem_bytes = c.smem_bytes;
