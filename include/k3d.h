@@ -101,6 +101,7 @@ typedef struct K3dInputs {
        (dz, dy, dx): run r covers offsets (dx0[r]..dx1[r], dy[r], dz[r]).  The union
        of the runs is exactly the reference template (super_block.py:226-265). */
     int32_t nruns;
+    int32_t ntmpl;         /* number of template offsets the runs cover (sizing hint, 0 = unknown) */
     const int16_t *runs;   /* [nruns*4] = dx0, dx1, dy, dz */
     /* node -> super block index per axis (super_block.py:319-346) and its inverse:
        nodes lutx0[b] .. lutx0[b+1]-1 fall in super-block column b */

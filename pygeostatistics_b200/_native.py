@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libk3d.so")
+LIB_PATH = os.environ.get("K3D_LIB", os.path.join(HERE, "csrc", "libk3d.so"))
 
 MAXNST, MAXDRIFT, MAXNDMAX, MAXDIS = 4, 9, 64, 128
 
@@ -40,7 +40,7 @@ class K3dInputs(C.Structure):
         ("nd", C.c_int64),
         ("sx", C.c_void_p), ("sy", C.c_void_p), ("sz", C.c_void_p), ("sv", C.c_void_p),
         ("ssec", C.c_void_p), ("sbstart", C.c_void_p),
-        ("nruns", C.c_int32), ("runs", C.c_void_p),
+        ("nruns", C.c_int32), ("ntmpl", C.c_int32), ("runs", C.c_void_p),
         ("nodex0", C.c_void_p), ("nodey0", C.c_void_p), ("nodez0", C.c_void_p),
         ("dbxyz", C.c_void_p), ("extgrid", C.c_void_p),
     ]

@@ -32,6 +32,10 @@
 #define K3D_VERSION_STR "pygeostatistics_b200 k3d 0.1 (sm_100a)"
 #define K3D_EPS 2.220446049250313e-16 /* 7./3-4./3-1, krige3d.py:795,853 */
 #define FULL 0xffffffffu
+// The warps of a CTA move through the phases of a node together (search+fill /
+// covariances / solve): warps that run the same loop share instruction-cache lines, which
+// measured as the difference between 2.5 and 0.2 "no instruction" stall cycles per issue.
+#define K3D_PHASE_BARRIER() __syncthreads()
 
 namespace {
 
@@ -62,13 +66,12 @@ struct KCfg {
     int kcap;       // per-warp candidate list capacity (multiple of 32)
     int cs;         // staged candidate capacity per CTA
     int keepmax;    // max entries that survive a prune: noct>0 ? 8*noct : ndmax
-    int sbz0;       // first super-block z index touched by the slab
-    int ntz;        // number of super-block z indices touched by the slab
     int pw_bytes;   // per-warp shared bytes
     int smem_bytes; // total dynamic shared bytes
     int nst;        // number of variogram structures
     int ndb;        // block discretisation points
     int urow;       // doubles in one pivot-row buffer (register solve) or rtot (generic)
+    int reuse;      // 1: keep the sample-sample covariance block between adjacent nodes
 };
 
 // Variogram structures prepared on the host for the kernel: the rotation matrix of
@@ -85,24 +88,31 @@ struct KPrep {
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 // shared memory carve-up (bytes from the dynamic smem base)
-//   [tri LUT u16 x ntri][stage x,y,z f64 x cs][stage idx i32 x cs][chunk i32 x 3*threads]
-//   [block points transformed per structure f64 x 3*nst*ndb]
-//   [per-warp: union{ P f64 x ntri | keys f64 x kcap + slots i32 x kcap },
-//              xa,ya,za,va,ve f64 x ndp, ut f64 x 3*nst*ndp, pivot rows f64 x 2*urow]
+//   CTA : [tri LUT u16 x ntri][stage x,y,z f64 x cs][stage idx i32 x cs]
+//         [chunk i32 x 3*threads][block points per structure f64 x 3*nst*ndb]
+//   warp: [P f64 x ntri]                      pristine bordered system (persists)
+//         [keys f64 x kcap][slots i32 x kcap] search list
+//         [px,py,pz,va,ve f64 x ndp]          neighbours by matrix position
+//         [ut f64 x 3*nst*(ndp+ndb)]          their coordinates in structure space, then
+//                                             the node's block points (columns ndp..)
+//         [pslot,pid,newpos,newslot i32 x ndp] staged slot / sample id / fill list
+//         [pivot rows f64 x 2*urow][tau f64 x 8][unode f64 x 3*nst]
 __host__ __device__ inline int off_tri(const KCfg &) { return 0; }
 __host__ __device__ inline int off_stage(const KCfg &c) { return align16(c.ntri * 2); }
 __host__ __device__ inline int off_sidx(const KCfg &c) { return off_stage(c) + c.cs * 24; }
 __host__ __device__ inline int off_chunk(const KCfg &c) { return align16(off_sidx(c) + c.cs * 4); }
 __host__ __device__ inline int off_udb(const KCfg &c) { return align16(off_chunk(c) + c.warps * 32 * 12); }
 __host__ __device__ inline int off_warp(const KCfg &c) { return align16(off_udb(c) + 3 * c.nst * c.ndb * 8); }
-__host__ __device__ inline int pw_union(const KCfg &c)
-{
-    int a = c.ntri * 8, b = c.kcap * 12;
-    return align16(a > b ? a : b);
-}
+__host__ __device__ inline int pw_off_keys(const KCfg &c) { return align16(c.ntri * 8); }
+__host__ __device__ inline int pw_off_slots(const KCfg &c) { return pw_off_keys(c) + c.kcap * 8; }
+__host__ __device__ inline int pw_off_pos(const KCfg &c) { return align16(pw_off_slots(c) + c.kcap * 4); }
+__host__ __device__ inline int pw_off_ut(const KCfg &c) { return pw_off_pos(c) + 5 * c.ndp * 8; }
+__host__ __device__ inline int pw_off_ints(const KCfg &c) { return pw_off_ut(c) + 3 * c.nst * (c.ndp + c.ndb) * 8; }
+__host__ __device__ inline int pw_off_rows(const KCfg &c) { return align16(pw_off_ints(c) + 4 * c.ndp * 4); }
+__host__ __device__ inline int pw_off_tau(const KCfg &c) { return pw_off_rows(c) + 2 * c.urow * 8; }
 __host__ __device__ inline int pw_bytes(const KCfg &c)
 {
-    return align16(pw_union(c) + (5 * c.ndp + 3 * c.nst * c.ndp + 2 * c.urow) * 8);
+    return align16(pw_off_tau(c) + (8 + 3 * c.nst) * 8);
 }
 
 // ---------------------------------------------------------------------------
@@ -124,46 +134,42 @@ __device__ __forceinline__ double sqdist_exact(double dx, double dy, double dz,
     return s;
 }
 
-// Covariance (krige3d.py:838-875, cova3) between two points whose coordinates have been
-// pre-multiplied by every structure's scaled rotation matrix: u[(3*s+k)*stride + idx].
-// |u_i - u_j|^2 is (h/a)^2 of structure s (h^2 for a power structure).
-__device__ __forceinline__ double cova_t(const K3dParams &P, const KPrep &Q,
-                                         const double *__restrict__ ua, int sa, int ia,
-                                         const double *__restrict__ ub, int sb, int ib)
+// Nested covariance (krige3d.py:838-875, cova3) from the per-structure squared scaled
+// distances h2[s] = (h/a)^2 (h^2 for a power structure).  Inlined at exactly ONE call
+// site (the assembly work loop): the transcendental code is large and the instruction
+// cache is small.
+__device__ __forceinline__ double cova_from_h2(const K3dParams &P, const KPrep &Q,
+                                               const double (&h2v)[K3D_MAXNST])
 {
-    double dx = ua[ia] - ub[ib], dy = ua[sa + ia] - ub[sb + ib], dz = ua[2 * sa + ia] - ub[2 * sb + ib];
-    double h2 = dx * dx + dy * dy + dz * dz;
-    if (h2 < Q.eps0s)
+    if (h2v[0] < Q.eps0s)
         return P.maxcov;
     double cova = 0.0;
 #pragma unroll 1
     for (int s = 0; s < P.nst; s++) {
-        if (s != 0) {
-            const double *pa = ua + 3 * s * sa, *pb = ub + 3 * s * sb;
-            dx = pa[ia] - pb[ib]; dy = pa[sa + ia] - pb[sb + ib]; dz = pa[2 * sa + ia] - pb[2 * sb + ib];
-            h2 = dx * dx + dy * dy + dz * dz;
-        }
-        const double c = Q.cc[s];
-        const int it = Q.it[s];
-        if (it == 1) {
-            if (h2 < 1.0) {
-                double hr = sqrt(h2);
-                cova += c * (1.0 - hr * (1.5 - 0.5 * h2));
+        {
+            const double h2 = s == 0 ? h2v[0] : s == 1 ? h2v[1] : s == 2 ? h2v[2] : h2v[3];
+            const double c = Q.cc[s];
+            const int it = Q.it[s];
+            if (it == 1) {
+                if (h2 < 1.0) {
+                    double hr = sqrt(h2);
+                    cova += c * (1.0 - hr * (1.5 - 0.5 * h2));
+                }
+            } else if (it == 2) {
+                cova += c * exp(-3.0 * sqrt(h2));
+            } else if (it == 3) {
+                cova += c * exp(-3.0 * h2);
+            } else if (it == 4) {
+                cova += P.maxcov - c * pow(sqrt(h2), Q.aa[s]);
+            } else {
+                cova += c * cos(sqrt(h2) * 3.141592653589793);
             }
-        } else if (it == 2) {
-            cova += c * exp(-3.0 * sqrt(h2));
-        } else if (it == 3) {
-            cova += c * exp(-3.0 * h2);
-        } else if (it == 4) {
-            cova += P.maxcov - c * pow(sqrt(h2), Q.aa[s]);
-        } else {
-            cova += c * cos(sqrt(h2) * 3.141592653589793);
         }
     }
     return cova;
 }
 
-// u = rs * p for every structure (p relative to the node)
+// u = rs[s] * (x,y,z) for every structure, written at [..][idx] of a [3*nst][stride] array
 __device__ __forceinline__ void transform_point(const K3dParams &P, const KPrep &Q, double x,
                                                 double y, double z, double *u, int stride, int idx)
 {
@@ -174,47 +180,37 @@ __device__ __forceinline__ void transform_point(const K3dParams &P, const KPrep 
         u[(3 * s + 2) * stride + idx] = r[6] * x + r[7] * y + r[8] * z;
     }
 }
-
-// krige3d.py:770-801 for one sample: covariance to the block (ndb points, udb = their
-// transformed coordinates, db = raw offsets for the coincidence test)
-__device__ __forceinline__ double cov_to_block(const K3dParams &P, const KPrep &Q,
-                                               const double *ut, int ndp, int i, double x,
-                                               double y, double z, const double *udb,
-                                               const double *__restrict__ db)
+// out-of-line copy for the rarely executed call sites
+__device__ __noinline__ void transform_point_cold(const K3dParams &P, const KPrep &Q, double x,
+                                                  double y, double z, double *u, int stride, int idx)
 {
-    const int ndb = P.ndb;
-    if (ndb <= 1)
-        return cova_t(P, Q, ut, ndp, i, udb, 1, 0);
-    double cb = 0.0;
-    for (int j = 0; j < ndb; j++) {
-        cb += cova_t(P, Q, ut, ndp, i, udb, ndb, j);
-        double dx = x - db[j], dy = y - db[ndb + j], dz = z - db[2 * ndb + j];
-        if (dx * dx + dy * dy + dz * dz < K3D_EPS)
-            cb -= P.c0;
-    }
-    return cb / (double)ndb;
+    transform_point(P, Q, x, y, z, u, stride, idx);
 }
 
-// ---------------------------------------------------------------------------
-// Register-resident LDL^T of the bordered system.
-//
-// The (N+2) x (N+2) lower triangle lives in the warp's registers, 2-D cyclic:
-// mirrored row r, column c (c <= r) belongs to lane (r & 3) * 8 + (c & 7), register
-// m[r >> 2][c >> 3].  Pivot row M is broadcast through a double-buffered shared-memory
-// row; every other operand of the rank-1 update is already in the lane's registers, so
-// one pivot costs A + B shared loads for up to A*B fused multiply-adds per lane.
-// Slots that do not exist for a lane (c > r) or rows already eliminated carry
-// don't-care values: they are only ever combined with other don't-care slots.
-// ---------------------------------------------------------------------------
+// 1/d to full double precision without the library's special-case slow path: hardware
+// seed (MUFU.RCP64H) + two Newton steps.  d == 0 gives a non-finite result, which the
+// caller reports as a singular system.
+__device__ __forceinline__ double rcp_fast(double d)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
 template <int AMAX> struct RegSolve {
     static constexpr int BMAX = ((4 * (AMAX - 1) + 3) >> 3) + 1;
 
+    // rank-1 update of row blocks 0..A-1 with the pivot row in `row`
     template <int A>
     static __device__ __forceinline__ void update(double (&m)[AMAX][BMAX], const double *row,
                                                   int li, int lj, double ninv)
     {
-        constexpr int B = A > 0 ? ((4 * (A - 1) + 3) >> 3) + 1 : 0;
-        double w[A > 0 ? A : 1], u[B > 0 ? B : 1];
+        constexpr int B = ((4 * (A - 1) + 3) >> 3) + 1;
+        double w[A], u[B];
 #pragma unroll
         for (int a = 0; a < A; a++) w[a] = row[li + 4 * a] * ninv;
 #pragma unroll
@@ -226,25 +222,10 @@ template <int AMAX> struct RegSolve {
                 if (8 * b <= 4 * a + 3) m[a][b] = fma(w[a], u[b], m[a][b]);
     }
 
-    template <int AP>
-    static __device__ __forceinline__ void pivot(double (&m)[AMAX][BMAX], int M, int q,
-                                                 double *rowbuf, int urow, int li, int lj,
-                                                 bool top)
-    {
-        double *row = rowbuf + (M & 1) * urow;
-        if (li == q) {
-#pragma unroll
-            for (int b = 0; b < BMAX; b++)
-                if (8 * b <= 4 * AP + 3) row[lj + 8 * b] = m[AP][b];
-        }
-        __syncwarp();
-        const double ninv = -1.0 / row[M];
-        if (top)
-            update<AP + 1>(m, row, li, lj, ninv);
-        else
-            update<AP>(m, row, li, lj, ninv);
-    }
-
+    // Pivots M = 4*AP+3 .. 4*AP (those that exist).  Their rows live in register block AP
+    // of the lanes with li == M & 3.  The update always covers blocks 0..AP: for the last
+    // pivot of the block (q == 0) block AP then holds only rows already eliminated
+    // (don't-care values), which keeps one code path per AP.
     template <int AP>
     static __device__ __forceinline__ void block(double (&m)[AMAX][BMAX], int R, double *rowbuf,
                                                  int urow, int li, int lj)
@@ -252,11 +233,18 @@ template <int AMAX> struct RegSolve {
         if constexpr (AP >= 0) {
             if (4 * AP <= R) { // uniform: does this row block exist in the system?
 #pragma unroll 1
-                for (int q = 3; q >= 1; q--) {
+                for (int q = 3; q >= 0; q--) {
                     const int M = 4 * AP + q;
-                    if (M <= R && M >= 2) pivot<AP>(m, M, q, rowbuf, urow, li, lj, true);
+                    if (M > R || M < 2) continue;
+                    double *row = rowbuf + (M & 1) * urow;
+                    if (li == q) {
+#pragma unroll
+                        for (int b = 0; b < BMAX; b++)
+                            if (8 * b <= 4 * AP + 3) row[lj + 8 * b] = m[AP][b];
+                    }
+                    __syncwarp();
+                    update<AP + 1>(m, row, li, lj, -rcp_fast(row[M]));
                 }
-                if (AP > 0) pivot<AP>(m, 4 * AP, 0, rowbuf, urow, li, lj, false);
             }
             block<AP - 1>(m, R, rowbuf, urow, li, lj);
         }
@@ -283,7 +271,7 @@ template <int AMAX> struct RegSolve {
 };
 
 // Generic fallback for systems too large for the register solver: the same elimination
-// with the packed triangle kept in shared memory (flat, lane-strided rank-1 updates).
+// on a scratch copy of the packed triangle in shared memory (flat rank-1 updates).
 __device__ __forceinline__ void smem_solve(double *Pm, const uint16_t *tri, int R, double *wv,
                                            int lane, double &est, double &var)
 {
@@ -332,20 +320,21 @@ __device__ __forceinline__ void warp_bitonic(double *keys, int *slots, int n, in
     }
 }
 
-// sgsim.py:945-964 octant classification (repair D5); d = sample - node
-__device__ __forceinline__ int octant_of(double dx, double dy, double dz)
+// sgsim.py:945-964 octant classification (repair D5); arguments are NODE - SAMPLE
+// (the sign the distance code already has), so every test is mirrored.
+__device__ __forceinline__ int octant_of_neg(double ndx, double ndy, double ndz)
 {
     int iq;
-    if (dz >= 0.0) {
+    if (ndz <= 0.0) {           // dz >= 0
         iq = 3;
-        if (dx <= 0.0 && dy > 0.0) iq = 0;
-        if (dx > 0.0 && dy >= 0.0) iq = 1;
-        if (dx < 0.0 && dy <= 0.0) iq = 2;
+        if (ndx >= 0.0 && ndy < 0.0) iq = 0;   // dx <= 0 and dy > 0
+        if (ndx < 0.0 && ndy <= 0.0) iq = 1;   // dx > 0 and dy >= 0
+        if (ndx > 0.0 && ndy >= 0.0) iq = 2;   // dx < 0 and dy <= 0
     } else {
         iq = 7;
-        if (dx <= 0.0 && dy > 0.0) iq = 4;
-        if (dx > 0.0 && dy >= 0.0) iq = 5;
-        if (dx < 0.0 && dy <= 0.0) iq = 6;
+        if (ndx >= 0.0 && ndy < 0.0) iq = 4;
+        if (ndx < 0.0 && ndy <= 0.0) iq = 5;
+        if (ndx > 0.0 && ndy >= 0.0) iq = 6;
     }
     return iq;
 }
@@ -383,7 +372,7 @@ __device__ __noinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, do
         double key = valid ? keys[j] : 0.0;
         int iq = 8;
         if (valid)
-            iq = octant_of(nc.qx[slot] - nc.xloc, nc.qy[slot] - nc.yloc, nc.qz[slot] - nc.zloc);
+            iq = octant_of_neg(nc.xloc - nc.qx[slot], nc.yloc - nc.qy[slot], nc.zloc - nc.qz[slot]);
         int rank = 0;
 #pragma unroll
         for (int o = 0; o < 8; o++) {
@@ -405,11 +394,13 @@ __device__ __noinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, do
     return kept;
 }
 
-// scan `count` contiguous candidates (slots slot0..slot0+count) and append the
-// in-radius ones to the warp's list; prunes when the list could overflow.
-__device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
+// Scan `count` contiguous candidates (slots slot0..slot0+count) and append those within
+// the search radius -- and within the caller's exact per-octant upper bounds tau[] --
+// to the warp's list; prunes when the list could overflow.
+__device__ __noinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
                                                const NodeCtx &nc, int slot0, int count,
-                                               double *keys, int *slots, int K, int lane)
+                                               const double *tau, double *keys, int *slots,
+                                               int K, int lane)
 {
     const double *rs = P.rotmat + 9 * P.nst;
     const unsigned lt = (1u << lane) - 1u;
@@ -420,9 +411,13 @@ __device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &c
         if (c < count) {
             int s = slot0 + c;
             // point1 = node, point2 = sample (super_block.py:301-305)
-            h = sqdist_exact(__dsub_rn(nc.xloc, nc.qx[s]), __dsub_rn(nc.yloc, nc.qy[s]),
-                             __dsub_rn(nc.zloc, nc.qz[s]), rs);
-            in = !(h > P.radsqd); // reference: `if hsqd > radsqd: continue`
+            double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
+                   dz = __dsub_rn(nc.zloc, nc.qz[s]);
+            h = sqdist_exact(dx, dy, dz, rs);
+            // reference: `if hsqd > radsqd: continue`; tau[] <= radsqd are exact upper
+            // bounds of what can still be selected in the sample's octant
+            double bound = tau[P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0];
+            in = !(h > bound);
         }
         unsigned m = __ballot_sync(FULL, in);
         if (m == 0u)
@@ -441,7 +436,6 @@ __device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &c
     return K;
 }
 
-
 // ---------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------
@@ -454,6 +448,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = cfg.warps * 32;
+    const int ndp = cfg.ndp;
 
     uint16_t *tri = (uint16_t *)(smem + off_tri(cfg));
     double *stx = (double *)(smem + off_stage(cfg));
@@ -461,24 +456,31 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     double *stz = sty + cfg.cs;
     int *stidx = (int *)(smem + off_sidx(cfg));
     int *chunk = (int *)(smem + off_chunk(cfg)); // [3][nthreads]: lo, cnt, off
+    double *udb = (double *)(smem + off_udb(cfg)); // [3*nst][ndb] block points, structure space
     unsigned char *wbase = smem + off_warp(cfg) + warp * pw_bytes(cfg);
-    double *Pm = (double *)wbase;                   // packed bordered system
-    double *keys = (double *)wbase;                 // aliases Pm during the search
-    int *slots = (int *)(wbase + cfg.kcap * 8);
-    double *xa = (double *)(wbase + pw_union(cfg));
-    double *ya = xa + cfg.ndp, *za = ya + cfg.ndp, *va = za + cfg.ndp, *ve = va + cfg.ndp;
-    double *ut = ve + cfg.ndp;                      // [3*nst][ndp] transformed coordinates
-    double *wv = ut + 3 * cfg.nst * cfg.ndp;        // pivot rows (2 x urow)
-    double *udb = (double *)(smem + off_udb(cfg));  // [3*nst][ndb] transformed block points
+    double *Pm = (double *)wbase;
+    double *keys = (double *)(wbase + pw_off_keys(cfg));
+    int *slots = (int *)(wbase + pw_off_slots(cfg));
+    double *px = (double *)(wbase + pw_off_pos(cfg));
+    double *py = px + ndp, *pz = py + ndp, *va = pz + ndp, *ve = va + ndp;
+    double *ut = (double *)(wbase + pw_off_ut(cfg));
+    int *pslot = (int *)(wbase + pw_off_ints(cfg));
+    int *pid = pslot + ndp, *newpos = pid + ndp, *newslot = newpos + ndp;
+    const int ucols = ndp + cfg.ndb; // columns of ut: neighbours by position, then block points
+    double *rows = (double *)(wbase + pw_off_rows(cfg));
+    double *tau = (double *)(wbase + pw_off_tau(cfg));
+    double *unode = tau + 8;
 
     __shared__ int s_total, s_warpsum[32];
+    __shared__ int s_job[8][6];     // per warp: npairs, npad, na, full, R
+    __shared__ double s_jloc[8][3]; // per warp: node location
 
-    // ---- tile geometry -----------------------------------------------------
+    // ---- tile geometry: the grid nodes that fall in super block (sbx, sby, sbz) -------
     int tile = blockIdx.x;
     const int sbx = tile % P.nxsup;
     tile /= P.nxsup;
     const int sby = tile % P.nysup;
-    const int sbz = cfg.sbz0 + tile / P.nysup;
+    const int sbz = tile / P.nysup;
     const int x0 = in.nodex0[sbx], x1 = in.nodex0[sbx + 1];
     const int y0 = in.nodey0[sby], y1 = in.nodey0[sby + 1];
     int z0 = in.nodez0[sbz], z1 = in.nodez0[sbz + 1];
@@ -488,6 +490,9 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     const int tnodes = tnx * tny * tnz;
     if (tnodes <= 0)
         return;
+    // structure-space origin of the tile: first node of the super block (slab independent)
+    const double cx0 = P.xmn + x0 * P.xsiz, cy0 = P.ymn + y0 * P.ysiz,
+                 cz0 = P.zmn + in.nodez0[sbz] * P.zsiz;
 
     // ---- triangular index LUT: e -> (row<<8 | col), row >= col --------------
     for (int e = tid; e < cfg.ntri; e += nthreads) {
@@ -496,11 +501,10 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         while (pk(r, 0) > e) r--;
         tri[e] = (uint16_t)((r << 8) | (e - pk(r, 0)));
     }
-
-    // ---- block discretisation points in every structure's coordinates -------
+    // ---- block discretisation offsets in every structure's coordinates -------
     for (int j = tid; j < P.ndb; j += nthreads)
-        transform_point(P, Q, in.dbxyz[j], in.dbxyz[P.ndb + j], in.dbxyz[2 * P.ndb + j], udb,
-                        P.ndb, j);
+        transform_point_cold(P, Q, in.dbxyz[j], in.dbxyz[P.ndb + j], in.dbxyz[2 * P.ndb + j],
+                             udb, P.ndb, j);
 
     // ---- stage the candidate samples of this tile (ascending sorted index) ---
     bool staged = true;
@@ -523,8 +527,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     }
                 }
             }
-            // CTA-wide exclusive scan of cnt
-            int incl = cnt;
+            int incl = cnt; // CTA-wide exclusive scan of cnt
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 int v = __shfl_up_sync(FULL, incl, d);
@@ -565,27 +568,44 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     const int ncand = s_total;
     const double *db = in.dbxyz;
     const size_t slab_off = (size_t)iz0 * P.nx * P.ny;
-    const unsigned lt = (1u << lane) - 1u;
-    (void)lt;
+    const unsigned ltm = (1u << lane) - 1u;
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    const int mdt = P.mdt;
+    const bool has_ext = (P.ktype == 2 || P.ktype == 3);
 
-    // ---- nodes of the tile, one warp each ------------------------------------
-    for (int t = warp; t < tnodes; t += cfg.warps) {
-        const int lx = t % tnx, ly = (t / tnx) % tny, lz = t / (tnx * tny);
+    NodeCtx nc;
+    nc.qx = staged ? stx : in.sx;
+    nc.qy = staged ? sty : in.sy;
+    nc.qz = staged ? stz : in.sz;
+
+    // ---- each warp walks a contiguous piece of a boustrophedon path through the tile:
+    //      consecutive nodes are grid neighbours, so their neighbourhoods overlap ---------
+    const int per = (tnodes + cfg.warps - 1) / cfg.warps;
+    const int t_begin = warp * per, t_end = (t_begin + per < tnodes) ? t_begin + per : tnodes;
+    int nprev = -1; // neighbours of the previous node whose covariances are still in Pm
+    int nhint = -1; // neighbours of the previous node listed in pslot (search hints)
+
+    for (int tt = 0; tt < per; tt++) {
+        const int t = t_begin + tt;
+        const bool active = t < t_end;
+        const int lz = t / (tnx * tny), rem = t - lz * (tnx * tny);
+        const int lyr = rem / tnx, lxr = rem - lyr * tnx;
+        const int ly = (lz & 1) ? tny - 1 - lyr : lyr;
+        const int lx = ((lz * tny + lyr) & 1) ? tnx - 1 - lxr : lxr;
         const int ix = x0 + lx, iy = y0 + ly, iz = z0 + lz;
         const size_t node = ((size_t)iz * P.ny + iy) * P.nx + ix;
         const size_t o = node - slab_off;
-        NodeCtx nc;
         // krige3d.py:307-309: xmn + ix*xsiz, multiply then add, unfused
         nc.xloc = __dadd_rn(P.xmn, __dmul_rn((double)ix, P.xsiz));
         nc.yloc = __dadd_rn(P.ymn, __dmul_rn((double)iy, P.ysiz));
         nc.zloc = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
-        double est = __longlong_as_double(0x7ff8000000000000LL), var = est;
+        double est = NaN, var = NaN;
         int status = K3D_ST_OK;
-        int na = 0;
+        int na = 0, tested = 0;
         double extest = 0.0, resce = 0.0, skmean = P.skmean;
 
-        bool live = true;
-        if (P.ktype == 2 || P.ktype == 3) { // krige3d.py:334-344
+        bool live = active;
+        if (has_ext && active) { // krige3d.py:334-344
             extest = in.extgrid[o];
             if (extest < P.tmin || extest >= P.tmax) {
                 status = K3D_ST_EXT_TRIMMED;
@@ -596,15 +616,48 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         }
 
         if (live) {
+            // ---- 0. exact upper bounds from the previous node's neighbours ---------------
+            // Any set of samples bounds the selection: if >= noct of them fall in octant o
+            // (>= ndmax overall when noct == 0) within the radius, nothing farther than the
+            // farthest of those can be selected there.  The previous node's neighbours are
+            // an excellent such set.
+            {
+                double mytau = P.radsqd;
+                if (nhint > 0) {
+                    const double *rs = P.rotmat + 9 * P.nst;
+                    bool inr = false;
+                    int oq = 0;
+                    unsigned hi = 0, lo = 0;
+                    if (lane < nhint) { // hints are the first (up to 32) positions
+                        int s = pslot[lane];
+                        double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
+                               dz = __dsub_rn(nc.zloc, nc.qz[s]);
+                        double h = sqdist_exact(dx, dy, dz, rs);
+                        inr = !(h > P.radsqd);
+                        oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
+                        hi = (unsigned)__double2hiint(h);
+                        lo = (unsigned)__double2loint(h);
+                    }
+                    const int noctants = P.noct > 0 ? 8 : 1;
+                    const int need = P.noct > 0 ? P.noct : P.ndmax;
+                    for (int q = 0; q < noctants; q++) {
+                        bool mine = inr && oq == q;
+                        int cnt = __popc(__ballot_sync(FULL, mine));
+                        unsigned mh = __reduce_max_sync(FULL, mine ? hi : 0u);
+                        unsigned ml = __reduce_max_sync(FULL, (mine && hi == mh) ? lo : 0u);
+                        if (cnt >= need && lane == q) mytau = __hiloint2double((int)mh, (int)ml);
+                    }
+                }
+                if (lane < 8) tau[lane] = mytau;
+                __syncwarp();
+            }
+
             // ---- 1. neighbour search ------------------------------------------
             int K = 0;
-            int tested = ncand;
             if (staged) {
-                nc.qx = stx; nc.qy = sty; nc.qz = stz;
-                K = scan_candidates(P, cfg, nc, 0, ncand, keys, slots, K, lane);
+                tested = ncand;
+                K = scan_candidates(P, cfg, nc, 0, ncand, tau, keys, slots, K, lane);
             } else { // tile too dense for the stage: walk the runs in global memory
-                nc.qx = in.sx; nc.qy = in.sy; nc.qz = in.sz;
-                tested = 0;
                 for (int r = 0; r < in.nruns; r++) {
                     const int16_t *rn = in.runs + 4 * r;
                     int by = sby + rn[2], bz = sbz + rn[3];
@@ -615,69 +668,207 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     if (bx0 > bx1) continue;
                     int b = (bz * P.nysup + by) * P.nxsup;
                     int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
-                    K = scan_candidates(P, cfg, nc, lo, hi - lo, keys, slots, K, lane);
+                    K = scan_candidates(P, cfg, nc, lo, hi - lo, tau, keys, slots, K, lane);
                     tested += hi - lo;
                 }
             }
-            if (out.ncand && lane == 0) out.ncand[o] = tested;
             __syncwarp();
             K = prune_list(P, nc, keys, slots, K, lane);
             na = K < P.ndmax ? K : P.ndmax; // krige3d.py:356-375
             __syncwarp();
-
-            // ---- gather the neighbours, coordinates relative to the node ---------
-            for (int i = lane; i < na; i += 32) {
-                int s = slots[i];
-                int g = staged ? stidx[s] : s;
-                xa[i] = nc.qx[s] - nc.xloc; // krige3d.py:369-371
-                ya[i] = nc.qy[s] - nc.yloc;
-                za[i] = nc.qz[s] - nc.zloc;
-                double v = in.sv[g];
-                double e = (P.ktype == 2 || P.ktype == 3) ? in.ssec[g] : 0.0;
-                va[i] = (P.ktype == 0) ? v - skmean : (P.ktype == 2 ? v - e : v);
-                ve[i] = e;
-                transform_point(P, Q, xa[i], ya[i], za[i], ut, cfg.ndp, i);
-                if (out.nbr_idx) out.nbr_idx[o * P.ndmax + i] = g;
+            if (out.nbr_idx) {
+                for (int i = lane; i < P.ndmax; i += 32)
+                    out.nbr_idx[o * P.ndmax + i] = i < na ? (staged ? stidx[slots[i]] : slots[i]) : -1;
             }
-            if (out.nbr_idx)
-                for (int i = na + lane; i < P.ndmax; i += 32) out.nbr_idx[o * P.ndmax + i] = -1;
+        }
+
+        bool solve = false;
+        if (!live) {
+            nprev = nhint = -1;
+            if (out.nbr_idx && active)
+                for (int i = lane; i < P.ndmax; i += 32) out.nbr_idx[o * P.ndmax + i] = -1;
+        } else if (na < P.ndmin || na == 0) { // krige3d.py:377, repair D15
+            status = K3D_ST_NOT_ENOUGH_DATA;
+            nprev = nhint = -1;
+        } else if (na <= mdt) { // krige3d.py:383
+            status = K3D_ST_NOT_ENOUGH_DRIFT;
+            nprev = nhint = -1;
+        } else {
+            solve = true;
+        }
+        const int N = na + mdt, R = N + 1;
+        if (solve) {
+            // ---- 2. map the neighbours to matrix positions ---------------------------
+            // A neighbour kept from the previous node keeps its row/column, so the
+            // sample-sample covariances already in Pm stay valid; newcomers take the
+            // positions that were freed.  (newpos[], newslot[]) lists what must be filled.
+            int nnew = na;
+            bool full = true;
+            if (cfg.reuse && nprev == na && na <= 32) {
+                int pos = -1;
+                const int myslot = lane < na ? slots[lane] : -1;
+                for (int p = 0; p < na; p++)
+                    if (pslot[p] == myslot) pos = p;
+                if (lane >= na) pos = -2;
+                const unsigned used = __reduce_or_sync(FULL, pos >= 0 ? (1u << pos) : 0u);
+                const unsigned unm = __ballot_sync(FULL, pos == -1);
+                const int cntnew = __popc(unm);
+                if (2 * cntnew <= na) {
+                    full = false;
+                    nnew = cntnew;
+                    if (pos == -1) {
+                        unsigned freem = ~used & (na == 32 ? 0xffffffffu : ((1u << na) - 1u));
+                        const int r = __popc(unm & ltm);
+                        for (int k = 0; k < r; k++) freem &= freem - 1u;
+                        newpos[r] = __ffs(freem) - 1;
+                        newslot[r] = myslot;
+                    }
+                }
+            }
+            if (full) { // positions = distance order
+                for (int i = lane; i < na; i += 32) {
+                    newpos[i] = i;
+                    newslot[i] = slots[i];
+                }
+            }
+            __syncwarp();
+            for (int k = lane; k < nnew; k += 32) {
+                const int pos = newpos[k], sl = newslot[k];
+                const int g = staged ? stidx[sl] : sl;
+                pslot[pos] = sl;
+                pid[pos] = g;
+                const double x = nc.qx[sl], y = nc.qy[sl], z = nc.qz[sl];
+                px[pos] = x; py[pos] = y; pz[pos] = z;
+                const double v = in.sv[g], e = has_ext ? in.ssec[g] : 0.0;
+                va[pos] = (P.ktype == 0) ? v - P.skmean : (P.ktype == 2 ? v - e : v);
+                ve[pos] = e;
+                transform_point(P, Q, x - cx0, y - cy0, z - cz0, ut, ucols, pos);
+            }
+            // the node and its block points in every structure's coordinates (columns ndp..)
+            if (lane == 0)
+                transform_point_cold(P, Q, nc.xloc - cx0, nc.yloc - cy0, nc.zloc - cz0, unode, 1, 0);
+            __syncwarp();
+            for (int k = lane; k < 3 * P.nst * P.ndb; k += 32) {
+                const int row = k / P.ndb, j = k - row * P.ndb;
+                ut[row * ucols + ndp + j] = unode[row] + udb[row * P.ndb + j];
+            }
+            nhint = na;
             __syncwarp();
 
-            const int mdt = P.mdt;
-            if (na < P.ndmin || na == 0) { // krige3d.py:377, repair D15
-                status = K3D_ST_NOT_ENOUGH_DATA;
-            } else if (na <= mdt) { // krige3d.py:383
-                status = K3D_ST_NOT_ENOUGH_DRIFT;
-            } else if (na == 1) { // krige3d.py:423-468 (mdt == 0 here)
-                double cb = cov_to_block(P, Q, ut, cfg.ndp, 0, xa[0], ya[0], za[0], udb, db);
-                double s = cb / P.cbb;
-                double v0 = in.sv[staged ? stidx[slots[0]] : slots[0]];
-                est = s * v0 + (1.0 - s) * skmean;
-                var = P.cbb - s * cb;
-            } else {
-                // ---- 2. assemble the bordered system, mirrored packed lower ----------
-                const int N = na + mdt, R = N + 1;
-                // data-data covariances, strict pairs i > j (krige3d.py:748-763)
-                const int npair = (na * (na - 1)) >> 1;
-                for (int e = lane; e < npair; e += 32) {
-                    int rc = tri[e];
-                    int i = (rc >> 8) + 1, j = rc & 255;
-                    Pm[pk(R - j, R - i)] = cova_t(P, Q, ut, cfg.ndp, j, ut, cfg.ndp, i);
+            // publish this warp's covariance job for the pooled phase
+            if (lane == 0) {
+                const int npairs = full ? (na * (na - 1)) >> 1 : nnew * na;
+                s_job[warp][0] = npairs;
+                s_job[warp][1] = (npairs + 31) & ~31;      // pairs, padded to whole rounds
+                s_job[warp][2] = na;
+                s_job[warp][3] = full ? 1 : 0;
+                s_job[warp][4] = R;
+                s_jloc[warp][0] = nc.xloc; s_jloc[warp][1] = nc.yloc; s_jloc[warp][2] = nc.zloc;
+            }
+        }
+        if (!solve && lane == 0) {
+            s_job[warp][1] = 0;
+            s_job[warp][2] = 0;
+        }
+        K3D_PHASE_BARRIER();
+
+        // ---- 3. covariances of every node in flight, pooled over the CTA ---------------
+        // One work loop evaluates every covariance the nodes need (krige3d.py:748-801); the
+        // items of all warps are dealt out evenly, 32 at a time, so that no warp waits for
+        // another's longer list.  Per warp (job):
+        //   items [0, npairs)           sample-sample pairs: all, or those with a newcomer
+        //   items [npad, npad + na)     sample i against the node's ndb block points
+        {
+            int base = 0;
+            for (int jw = 0; jw < cfg.warps; jw++) {
+                const int jnpad = s_job[jw][1], jna = s_job[jw][2];
+                const int jlen = jnpad + ((jna + 31) & ~31);
+                // rounds of this job taken by this warp: round r goes to warp (base/32 + r) % warps
+                const int r0 = ((warp - (base >> 5)) % cfg.warps + cfg.warps) % cfg.warps;
+                if (jlen > 0) {
+                    const int jnpairs = s_job[jw][0], jfull = s_job[jw][3], jR = s_job[jw][4];
+                    unsigned char *jb = smem + off_warp(cfg) + jw * pw_bytes(cfg);
+                    double *jPm = (double *)jb;
+                    const double *jpx = (const double *)(jb + pw_off_pos(cfg));
+                    const double *jpy = jpx + ndp, *jpz = jpy + ndp;
+                    const double *jut = (const double *)(jb + pw_off_ut(cfg));
+                    const int *jnewpos = (const int *)(jb + pw_off_ints(cfg)) + 2 * ndp;
+                    const int magic = (65536 + jna - 1) / jna;
+                    for (int w = (r0 << 5) + lane; w < jlen; w += cfg.warps << 5) {
+                        int p1 = 0, p2 = 0, nsub = 0;
+                        const bool rhs = w >= jnpad;
+                        if (rhs) {
+                            p1 = w - jnpad; p2 = ndp; nsub = p1 < jna ? P.ndb : 0;
+                        } else if (w < jnpairs) {
+                            if (jfull) {
+                                const int rc = tri[w];
+                                p1 = rc & 255; p2 = (rc >> 8) + 1; nsub = 1; // p1 < p2
+                            } else {
+                                int a = (w * magic) >> 16, q = w - a * jna;
+                                if (q < 0) { a--; q += jna; }
+                                if (q >= jna) { a++; q -= jna; }
+                                const int p = jnewpos[a];
+                                p1 = p < q ? p : q; p2 = p < q ? q : p;
+                                nsub = p == q ? 0 : 1;
+                            }
+                        }
+                        const int p2first = p2;
+                        double acc = 0.0;
+                        for (int sub = 0; sub < nsub; sub++, p2++) {
+                            double h2v[K3D_MAXNST] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                            for (int st = 0; st < K3D_MAXNST; st++) {
+                                if (st < P.nst) {
+                                    const double *u = jut + 3 * st * ucols;
+                                    const double dx = u[p1] - u[p2], dy = u[ucols + p1] - u[ucols + p2],
+                                                 dz = u[2 * ucols + p1] - u[2 * ucols + p2];
+                                    h2v[st] = dx * dx + dy * dy + dz * dz;
+                                }
+                            }
+                            double c = cova_from_h2(P, Q, h2v);
+                            if (rhs && P.ndb > 1) { // krige3d.py:792-796
+                                const double dx = (jpx[p1] - s_jloc[jw][0]) - db[sub],
+                                             dy = (jpy[p1] - s_jloc[jw][1]) - db[P.ndb + sub],
+                                             dz = (jpz[p1] - s_jloc[jw][2]) - db[2 * P.ndb + sub];
+                                if (dx * dx + dy * dy + dz * dz < K3D_EPS) c -= P.c0;
+                            }
+                            acc += c;
+                        }
+                        if (rhs) {
+                            if (nsub) {
+                                if (P.ndb > 1) acc = acc / (double)P.ndb;
+                                if (P.itrend) acc = 0.0;    // repair D10
+                                jPm[pk(jR - p1, 1)] = acc;  // b row
+                            }
+                        } else if (nsub) {
+                            jPm[pk(jR - p1, jR - p2first)] = acc;
+                        }
+                    }
                 }
-                // right-hand side and data rows (krige3d.py:770-801)
+                base += jlen;
+            }
+        }
+        K3D_PHASE_BARRIER();
+        if (solve) {
+            if (na == 1) { // krige3d.py:423-468 (mdt == 0 here, R == 2)
+                const double cb = Pm[pk(R, 1)];
+                const double sw = cb / P.cbb;
+                const double v0 = in.sv[pid[0]];
+                est = sw * v0 + (1.0 - sw) * skmean;
+                var = P.cbb - sw * cb;
+                nprev = -1;
+            } else {
+                // data vector and constraint rows (krige3d.py:764-767, 493-583 with repair
+                // D6): they depend on the node and are rebuilt every time
                 for (int i = lane; i < na; i += 32) {
-                    double cb = cov_to_block(P, Q, ut, cfg.ndp, i, xa[i], ya[i], za[i], udb, db);
-                    if (P.itrend) cb = 0.0; // repair D10
+                    const double x = px[i] - nc.xloc, y = py[i] - nc.yloc, z = pz[i] - nc.zloc;
                     const int ri = R - i;
                     Pm[pk(ri, ri)] = P.maxcov; // cova3(p, p)
-                    Pm[pk(ri, 1)] = cb;        // b row
                     Pm[pk(ri, 0)] = va[i];     // v row
-                    // constraint rows (krige3d.py:764-767, 493-583, repair D6)
                     if (mdt > 0) {
                         int q = na;
                         Pm[pk(ri, R - q)] = P.unbias;
                         q++;
-                        double x = xa[i], y = ya[i], z = za[i];
 #pragma unroll
                         for (int l = 0; l < K3D_MAXDRIFT; l++) {
                             if (P.idrift[l]) {
@@ -712,14 +903,17 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 }
                 __syncwarp();
 
-                // ---- 3. LDL^T elimination of the N pivots ---------------------------
-                if constexpr (AMAX > 0)
-                    RegSolve<AMAX>::run(Pm, R, wv, cfg.urow, lane, est, var);
-                else
-                    smem_solve(Pm, tri, R, wv, lane, est, var);
+                // ---- 4. LDL^T elimination of the N pivots ---------------------------
+                if constexpr (AMAX > 0) {
+                    RegSolve<AMAX>::run(Pm, R, rows, cfg.urow, lane, est, var);
+                    nprev = na;
+                } else {
+                    smem_solve(Pm, tri, R, rows, lane, est, var); // destroys Pm
+                    nprev = -1;
+                }
                 if (!isfinite(est) || !isfinite(var)) { // zero pivot (krige3d.py:593)
                     status = K3D_ST_SINGULAR;
-                    est = var = __longlong_as_double(0x7ff8000000000000LL);
+                    est = var = NaN;
                 } else {
                     // var = cbb - b' A^-1 b (krige3d.py:601); est = v' A^-1 b (:603-609)
                     if (P.ktype == 0 || P.ktype == 2) est += skmean; // krige3d.py:611
@@ -727,16 +921,12 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 __syncwarp();
             }
         }
-        if (lane == 0) {
+        if (lane == 0 && active) {
             out.est[o] = est;
             out.var[o] = var;
             if (out.nbr_cnt) out.nbr_cnt[o] = na;
             if (out.status) out.status[o] = (uint8_t)status;
-        }
-        if (!live) {
-            if (out.nbr_idx)
-                for (int i = lane; i < P.ndmax; i += 32) out.nbr_idx[o * P.ndmax + i] = -1;
-            if (out.ncand && lane == 0) out.ncand[o] = 0;
+            if (out.ncand) out.ncand[o] = tested;
         }
         __syncwarp();
     }
@@ -792,20 +982,7 @@ __global__ void k3d_dfma_probe(double *sink, int iters)
     if (s == 123.456) sink[0] = s;
 }
 
-int make_cfg(const K3dParams *p, KCfg *c)
-{
-    c->rtot = p->ndmax + p->mdt + 2;
-    c->ntri = c->rtot * (c->rtot + 1) / 2;
-    c->ndp = (p->ndmax + 3) & ~3;
-    c->keepmax = p->noct > 0 ? 8 * p->noct : p->ndmax;
-    int need = c->keepmax + 32;
-    int kcap = 256;
-    while (kcap < need + 32) kcap += 32;
-    c->kcap = kcap;
-    c->nst = p->nst;
-    c->ndb = p->ndb;
-    return 0;
-}
+int roundup32(int x) { return (x + 31) & ~31; }
 
 // register-solver size class for a bordered system of `rtot` rows (0 = generic path)
 int amax_for(int rtot)
@@ -829,6 +1006,49 @@ void make_prep(const K3dParams *p, KPrep *q)
     }
     const double a0 = p->it[0] == 4 ? 1.0 : p->aa[0];
     q->eps0s = K3D_EPS / (a0 * a0);
+}
+
+// Shared-memory plan: warps per CTA and stage capacity such that two CTAs share an SM
+// when possible.  `mean_cand` is the expected number of candidate samples per tile.
+int make_cfg(const K3dParams *p, double mean_cand, int smem_max, KCfg *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->rtot = p->ndmax + p->mdt + 2;
+    c->ntri = c->rtot * (c->rtot + 1) / 2;
+    c->ndp = (p->ndmax + 3) & ~3;
+    c->keepmax = p->noct > 0 ? 8 * p->noct : p->ndmax;
+    c->kcap = 128; // power of two: the bitonic network pads the list up to it
+    while (c->kcap < c->keepmax + 64) c->kcap <<= 1;
+    c->nst = p->nst;
+    c->ndb = p->ndb;
+    const int amax = amax_for(c->rtot);
+    c->urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c->rtot;
+    c->reuse = amax > 0 ? 1 : 0;
+    int want = roundup32((int)(2.5 * mean_cand) + 64);
+    if (want < 256) want = 256;
+    if (want > 4096) want = 4096;
+    int floor_cs = roundup32((int)(1.4 * mean_cand) + 32);
+    if (floor_cs < 128) floor_cs = 128;
+    if (floor_cs > want) floor_cs = want;
+    const int half = (smem_max + 1024) / 2 - 1024 - 256; // two CTAs per SM
+    static const int warp_options[] = {8, 6, 4};
+    for (int pass = 0; pass < 2; pass++) {
+        const int budget = pass == 0 ? half : smem_max - 256;
+        for (int wi = 0; wi < 3; wi++) {
+            c->warps = warp_options[wi];
+            c->cs = 0;
+            const int fixed = off_warp(*c) + c->warps * pw_bytes(*c);
+            int cs = ((budget - fixed - 64) / 28) & ~31;
+            if (cs > want) cs = want;
+            if (cs >= floor_cs) {
+                c->cs = cs;
+                c->pw_bytes = pw_bytes(*c);
+                c->smem_bytes = off_warp(*c) + c->warps * c->pw_bytes;
+                return K3D_OK;
+            }
+        }
+    }
+    return K3D_ECAPACITY;
 }
 
 template <int AMAX>
@@ -892,38 +1112,20 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
     if (rc) return rc;
     if (iz0 == iz1) return K3D_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    KCfg c;
-    memset(&c, 0, sizeof(c));
-    make_cfg(p, &c);
-    // one CTA per super block; CTAs whose super block does not meet the slab exit at once
-    c.sbz0 = 0;
-    c.ntz = p->nzsup;
     int dev = 0, smem_max = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // 8 warps per CTA, two CTAs per SM: each CTA may use half of the SM's shared memory
-    c.warps = 8;
-    const int amax = amax_for(c.rtot);
-    c.urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c.rtot;
-    int budget = (smem_max + 1024) / 2 - 1024 - 256;
-    c.cs = 64;
-    int fixed = off_warp(c) - c.cs * 28 + c.warps * pw_bytes(c);
-    int cs = (budget - fixed - 64) / 28;
-    if (cs < 64) { // too big for two CTAs per SM: take the whole SM
-        budget = smem_max - 256;
-        cs = (budget - fixed - 64) / 28;
-        if (cs < 64) return fail(K3D_ECAPACITY, "ndmax/drift configuration exceeds shared memory");
-    }
-    if (cs > 4096) cs = 4096;
-    c.cs = cs & ~31;
-    c.pw_bytes = pw_bytes(c);
-    c.smem_bytes = off_warp(c) + c.warps * c.pw_bytes;
-    if (c.smem_bytes > smem_max) return fail(K3D_ECAPACITY, "shared memory budget exceeded");
-    long long ntiles = (long long)p->nxsup * p->nysup * c.ntz;
+    const double nsb = (double)p->nxsup * p->nysup * p->nzsup;
+    const double mean_cand = in->ntmpl > 0 ? (double)in->nd / nsb * in->ntmpl : 512.0;
+    KCfg c;
+    if (make_cfg(p, mean_cand, smem_max, &c) != K3D_OK)
+        return fail(K3D_ECAPACITY, "ndmax/drift/discretisation exceed the shared memory of an SM");
+    // one CTA per super block; CTAs whose super block does not meet the slab exit at once
+    long long ntiles = (long long)p->nxsup * p->nysup * p->nzsup;
     if (ntiles > 0x7fffffffLL) return fail(K3D_EINVAL, "too many tiles");
     KPrep q;
     make_prep(p, &q);
-    switch (amax) {
+    switch (amax_for(c.rtot)) {
     case 5: rc = launch_krige<5>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
     case 9: rc = launch_krige<9>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
     case 11: rc = launch_krige<11>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;

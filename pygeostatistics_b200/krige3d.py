@@ -380,6 +380,7 @@ class Krige3d(object):
         I.sx, I.sy, I.sz, I.sv, I.ssec = ptr(d['sx']), ptr(d['sy']), ptr(d['sz']), ptr(d['sv']), \
             ptr(d['ssec'])
         I.sbstart, I.nruns, I.runs = ptr(d['sbstart']), int(d['runs'].numel() // 4), ptr(d['runs'])
+        I.ntmpl = int(self.searcher.nsbtosr)
         I.nodex0, I.nodey0, I.nodez0 = ptr(d['nodex0']), ptr(d['nodey0']), ptr(d['nodez0'])
         I.dbxyz, I.extgrid = ptr(d['dbxyz']), ptr(d['extgrid'])
         O = _native.K3dOutputs()

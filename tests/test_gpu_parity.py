@@ -279,6 +279,7 @@ def test_host_buffer_c_abi_entry():
     for name in ('sx', 'sy', 'sz', 'sv', 'sbstart', 'runs', 'nodex0', 'nodey0', 'nodez0', 'dbxyz'):
         setattr(I, name, arrs[name].ctypes.data)
     I.nruns = len(s.runs)
+    I.ntmpl = s.nsbtosr
     plane = par['nx'] * par['ny']
     est = np.empty(plane * par['nz']); var = np.empty_like(est)
     half = par['nz'] // 2
@@ -287,5 +288,7 @@ def test_host_buffer_c_abi_entry():
         O.est = est[a * plane:].ctypes.data
         O.var = var[a * plane:].ctypes.data
         _native.check(_native.lib().k3d_krige_slab_host(C.byref(P), C.byref(I), a, b, C.byref(O)))
-    assert np.array_equal(est, k.estimation, equal_nan=True)
-    assert np.array_equal(var, k.estimation_variance, equal_nan=True)
+    # not bit-identical: each slab walks its own node path, so the rows of a system can
+    # be ordered differently (covariance reuse); the values agree to rounding
+    assert np.allclose(est, k.estimation, rtol=1e-11, atol=1e-12, equal_nan=True)
+    assert np.allclose(var, k.estimation_variance, rtol=1e-11, atol=1e-12, equal_nan=True)
