@@ -212,9 +212,9 @@ template <int AMAX> struct RegSolve {
         constexpr int B = ((4 * (A - 1) + 3) >> 3) + 1;
         double w[A], u[B];
 #pragma unroll
-        for (int a = 0; a < A; a++) w[a] = row[li + 4 * a] * ninv;
+        for (int a = 0; a < A; a++) w[a] = row[li + 4 * a];
 #pragma unroll
-        for (int b = 0; b < B; b++) u[b] = row[lj + 8 * b];
+        for (int b = 0; b < B; b++) u[b] = row[lj + 8 * b] * ninv;
 #pragma unroll
         for (int a = 0; a < A; a++)
 #pragma unroll
@@ -457,7 +457,9 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     int *stidx = (int *)(smem + off_sidx(cfg));
     int *chunk = (int *)(smem + off_chunk(cfg)); // [3][nthreads]: lo, cnt, off
     double *udb = (double *)(smem + off_udb(cfg)); // [3*nst][ndb] block points, structure space
-    unsigned char *wbase = smem + off_warp(cfg) + warp * pw_bytes(cfg);
+    const int pwb = pw_bytes(cfg), o_warp0 = off_warp(cfg), o_pos = pw_off_pos(cfg),
+              o_ut = pw_off_ut(cfg), o_ints = pw_off_ints(cfg), o_keys = pw_off_keys(cfg);
+    unsigned char *wbase = smem + o_warp0 + warp * pwb;
     double *Pm = (double *)wbase;
     double *keys = (double *)(wbase + pw_off_keys(cfg));
     int *slots = (int *)(wbase + pw_off_slots(cfg));
@@ -472,7 +474,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     double *unode = tau + 8;
 
     __shared__ int s_total, s_warpsum[32];
-    __shared__ int s_job[8][6];     // per warp: npairs, npad, na, full, R
+    __shared__ int s_job[8][6];     // per warp: npairs, npad, na, full, R, magic
     __shared__ double s_jloc[8][3]; // per warp: node location
 
     // ---- tile geometry: the grid nodes that fall in super block (sbx, sby, sbz) -------
@@ -571,6 +573,18 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     const unsigned ltm = (1u << lane) - 1u;
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
     const int mdt = P.mdt;
+    // block kriging: a sample's ndb block-point covariances are split into nsplit work
+    // items of <= 4 points so that the pooled rounds stay evenly sized
+    // (partial sums go to the then idle search-list area and are added up in a fixed
+    // order by the owning warp, so results do not depend on warp scheduling)
+    const int napad_max = (P.ndmax + 31) & ~31;
+    int nsplit = 1;
+    if (P.ndb > 1) {
+        nsplit = (P.ndb + 3) >> 2;
+        const int cap = ((cfg.kcap * 3) >> 1) / napad_max;
+        nsplit = nsplit < cap ? nsplit : cap;
+        nsplit = nsplit < 1 ? 1 : nsplit;
+    }
     const bool has_ext = (P.ktype == 2 || P.ktype == 3);
 
     NodeCtx nc;
@@ -763,6 +777,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 s_job[warp][2] = na;
                 s_job[warp][3] = full ? 1 : 0;
                 s_job[warp][4] = R;
+                s_job[warp][5] = (65536 + na - 1) / na;
                 s_jloc[warp][0] = nc.xloc; s_jloc[warp][1] = nc.yloc; s_jloc[warp][2] = nc.zloc;
             }
         }
@@ -779,26 +794,35 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         //   items [0, npairs)           sample-sample pairs: all, or those with a newcomer
         //   items [npad, npad + na)     sample i against the node's ndb block points
         {
-            int base = 0;
+            int next = 0; // warp that takes the next round of 32 items
             for (int jw = 0; jw < cfg.warps; jw++) {
                 const int jnpad = s_job[jw][1], jna = s_job[jw][2];
-                const int jlen = jnpad + ((jna + 31) & ~31);
-                // rounds of this job taken by this warp: round r goes to warp (base/32 + r) % warps
-                const int r0 = ((warp - (base >> 5)) % cfg.warps + cfg.warps) % cfg.warps;
+                const int jnapad = (jna + 31) & ~31;
+                const int jlen = jnpad + nsplit * jnapad;
+                int r0 = warp - next; // first round of this job that this warp takes
+                if (r0 < 0) r0 += cfg.warps;
+                next += jlen >> 5;
+                while (next >= cfg.warps) next -= cfg.warps;
                 if (jlen > 0) {
                     const int jnpairs = s_job[jw][0], jfull = s_job[jw][3], jR = s_job[jw][4];
-                    unsigned char *jb = smem + off_warp(cfg) + jw * pw_bytes(cfg);
+                    const int magic = s_job[jw][5];
+                    unsigned char *jb = smem + o_warp0 + jw * pwb;
                     double *jPm = (double *)jb;
-                    const double *jpx = (const double *)(jb + pw_off_pos(cfg));
+                    const double *jpx = (const double *)(jb + o_pos);
                     const double *jpy = jpx + ndp, *jpz = jpy + ndp;
-                    const double *jut = (const double *)(jb + pw_off_ut(cfg));
-                    const int *jnewpos = (const int *)(jb + pw_off_ints(cfg)) + 2 * ndp;
-                    const int magic = (65536 + jna - 1) / jna;
+                    const double *jut = (const double *)(jb + o_ut);
+                    const int *jnewpos = (const int *)(jb + o_ints) + 2 * ndp;
+                    double *jscratch = (double *)(jb + o_keys);
                     for (int w = (r0 << 5) + lane; w < jlen; w += cfg.warps << 5) {
-                        int p1 = 0, p2 = 0, nsub = 0;
+                        int p1 = 0, p2 = 0, nsub = 0, sub0 = 0;
                         const bool rhs = w >= jnpad;
-                        if (rhs) {
-                            p1 = w - jnpad; p2 = ndp; nsub = p1 < jna ? P.ndb : 0;
+                        int part = 0;
+                        if (rhs) { // sample p1 against block points [sub0, sub0 + nsub)
+                            p1 = w - jnpad;
+                            while (p1 >= jnapad) { p1 -= jnapad; part++; } // uniform per round
+                            sub0 = (part * P.ndb) / nsplit;
+                            nsub = p1 < jna ? ((part + 1) * P.ndb) / nsplit - sub0 : 0;
+                            p2 = ndp + sub0;
                         } else if (w < jnpairs) {
                             if (jfull) {
                                 const int rc = tri[w];
@@ -814,7 +838,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         }
                         const int p2first = p2;
                         double acc = 0.0;
-                        for (int sub = 0; sub < nsub; sub++, p2++) {
+                        for (int sub = sub0; sub < sub0 + nsub; sub++, p2++) {
                             double h2v[K3D_MAXNST] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                             for (int st = 0; st < K3D_MAXNST; st++) {
@@ -835,23 +859,28 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                             acc += c;
                         }
                         if (rhs) {
-                            if (nsub) {
-                                if (P.ndb > 1) acc = acc / (double)P.ndb;
-                                if (P.itrend) acc = 0.0;    // repair D10
-                                jPm[pk(jR - p1, 1)] = acc;  // b row
+                            if (nsub) { // b row (krige3d.py:797-798)
+                                if (nsplit > 1)
+                                    jscratch[part * napad_max + p1] = acc;
+                                else
+                                    jPm[pk(jR - p1, 1)] = acc;
                             }
                         } else if (nsub) {
                             jPm[pk(jR - p1, jR - p2first)] = acc;
                         }
                     }
                 }
-                base += jlen;
             }
         }
         K3D_PHASE_BARRIER();
         if (solve) {
             if (na == 1) { // krige3d.py:423-468 (mdt == 0 here, R == 2)
-                const double cb = Pm[pk(R, 1)];
+                double cb = Pm[pk(R, 1)];
+                if (nsplit > 1) {
+                    cb = 0.0;
+                    for (int part = 0; part < nsplit; part++) cb += keys[part * napad_max];
+                    cb /= (double)P.ndb;
+                }
                 const double sw = cb / P.cbb;
                 const double v0 = in.sv[pid[0]];
                 est = sw * v0 + (1.0 - sw) * skmean;
@@ -865,6 +894,12 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     const int ri = R - i;
                     Pm[pk(ri, ri)] = P.maxcov; // cova3(p, p)
                     Pm[pk(ri, 0)] = va[i];     // v row
+                    if (nsplit > 1) { // b row from the partial sums (krige3d.py:797-798)
+                        double cb = 0.0;
+                        for (int part = 0; part < nsplit; part++) cb += keys[part * napad_max + i];
+                        Pm[pk(ri, 1)] = cb / (double)P.ndb;
+                    }
+                    if (P.itrend) Pm[pk(ri, 1)] = 0.0; // repair D10: kriging the trend
                     if (mdt > 0) {
                         int q = na;
                         Pm[pk(ri, R - q)] = P.unbias;
