@@ -97,6 +97,7 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 //                                             the node's block points (columns ndp..)
 //         [pslot,pid,newpos,newslot i32 x ndp] staged slot / sample id / fill list
 //         [pivot rows f64 x 2*urow][tau f64 x 8][unode f64 x 3*nst]
+//         [hint i32 x 64]                     previous node's nearest candidates (slots)
 __host__ __device__ inline int off_tri(const KCfg &) { return 0; }
 __host__ __device__ inline int off_stage(const KCfg &c) { return align16(c.ntri * 2); }
 __host__ __device__ inline int off_sidx(const KCfg &c) { return off_stage(c) + c.cs * 24; }
@@ -110,9 +111,10 @@ __host__ __device__ inline int pw_off_ut(const KCfg &c) { return pw_off_pos(c) +
 __host__ __device__ inline int pw_off_ints(const KCfg &c) { return pw_off_ut(c) + 3 * c.nst * (c.ndp + c.ndb) * 8; }
 __host__ __device__ inline int pw_off_rows(const KCfg &c) { return align16(pw_off_ints(c) + 4 * c.ndp * 4); }
 __host__ __device__ inline int pw_off_tau(const KCfg &c) { return pw_off_rows(c) + 2 * c.urow * 8; }
+__host__ __device__ inline int pw_off_hint(const KCfg &c) { return pw_off_tau(c) + (8 + 3 * c.nst) * 8; }
 __host__ __device__ inline int pw_bytes(const KCfg &c)
 {
-    return align16(pw_off_tau(c) + (8 + 3 * c.nst) * 8);
+    return align16(pw_off_hint(c) + 64 * 4);
 }
 
 // ---------------------------------------------------------------------------
@@ -346,8 +348,10 @@ struct NodeCtx {
 
 // Sort the K collected candidates and keep what the reference would keep:
 // noct == 0 -> the ndmax nearest; noct > 0 -> per-octant nearest noct, at most 8*noct.
+// When `hint` is given, the (up to 64) nearest candidates are copied there in distance
+// order before the octant rule thins them: they seed the next node's bounds.
 __device__ __noinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, double *keys,
-                                       int *slots, int K, int lane)
+                                       int *slots, int K, int lane, int *hint = nullptr)
 {
     if (K > 1) {
         int n = 32;
@@ -358,6 +362,10 @@ __device__ __noinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, do
         }
         __syncwarp();
         warp_bitonic(keys, slots, n, lane);
+    }
+    if (hint) {
+        const int nh = K < 64 ? K : 64;
+        for (int t = lane; t < nh; t += 32) hint[t] = slots[t];
     }
     if (P.noct <= 0)
         return K < P.ndmax ? K : P.ndmax;
@@ -472,6 +480,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     double *rows = (double *)(wbase + pw_off_rows(cfg));
     double *tau = (double *)(wbase + pw_off_tau(cfg));
     double *unode = tau + 8;
+    int *hint = (int *)(wbase + pw_off_hint(cfg));
 
     __shared__ int s_total, s_warpsum[32];
     __shared__ int s_job[8][6];     // per warp: npairs, npad, na, full, R, magic
@@ -597,7 +606,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     const int per = (tnodes + cfg.warps - 1) / cfg.warps;
     const int t_begin = warp * per, t_end = (t_begin + per < tnodes) ? t_begin + per : tnodes;
     int nprev = -1; // neighbours of the previous node whose covariances are still in Pm
-    int nhint = -1; // neighbours of the previous node listed in pslot (search hints)
+    int nhint = -1; // previous node's nearest candidates listed in hint[]
 
     for (int tt = 0; tt < per; tt++) {
         const int t = t_begin + tt;
@@ -630,37 +639,48 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         }
 
         if (live) {
-            // ---- 0. exact upper bounds from the previous node's neighbours ---------------
-            // Any set of samples bounds the selection: if >= noct of them fall in octant o
-            // (>= ndmax overall when noct == 0) within the radius, nothing farther than the
-            // farthest of those can be selected there.  The previous node's neighbours are
-            // an excellent such set.
+            // ---- 0. exact upper bounds from the previous node's candidates ----------------
+            // Any set of samples bounds the selection: once `need` of them (noct per octant,
+            // or ndmax overall) are seen within the radius in an octant, nothing farther than
+            // the farthest of those can be selected there.  The previous node's nearest
+            // candidates, taken in their old distance order, give almost tight bounds.
             {
                 double mytau = P.radsqd;
                 if (nhint > 0) {
                     const double *rs = P.rotmat + 9 * P.nst;
-                    bool inr = false;
-                    int oq = 0;
-                    unsigned hi = 0, lo = 0;
-                    if (lane < nhint) { // hints are the first (up to 32) positions
-                        int s = pslot[lane];
-                        double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
-                               dz = __dsub_rn(nc.zloc, nc.qz[s]);
-                        double h = sqdist_exact(dx, dy, dz, rs);
-                        inr = !(h > P.radsqd);
-                        oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
-                        hi = (unsigned)__double2hiint(h);
-                        lo = (unsigned)__double2loint(h);
-                    }
                     const int noctants = P.noct > 0 ? 8 : 1;
                     const int need = P.noct > 0 ? P.noct : P.ndmax;
-                    for (int q = 0; q < noctants; q++) {
-                        bool mine = inr && oq == q;
-                        int cnt = __popc(__ballot_sync(FULL, mine));
-                        unsigned mh = __reduce_max_sync(FULL, mine ? hi : 0u);
-                        unsigned ml = __reduce_max_sync(FULL, (mine && hi == mh) ? lo : 0u);
-                        if (cnt >= need && lane == q) mytau = __hiloint2double((int)mh, (int)ml);
+                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    unsigned bh = 0, bl = 0; // lane q: running max of octant q's first `need`
+                    for (int h0 = 0; h0 < nhint; h0 += 32) {
+                        bool inr = false;
+                        int oq = 0;
+                        unsigned hi = 0, lo = 0;
+                        if (h0 + lane < nhint) {
+                            const int s = hint[h0 + lane];
+                            double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
+                                   dz = __dsub_rn(nc.zloc, nc.qz[s]);
+                            double h = sqdist_exact(dx, dy, dz, rs);
+                            inr = !(h > P.radsqd);
+                            oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
+                            hi = (unsigned)__double2hiint(h);
+                            lo = (unsigned)__double2loint(h);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            if (q < noctants) {
+                                const unsigned mq = __ballot_sync(FULL, inr && oq == q);
+                                const bool mine = inr && oq == q && cnt[q] + __popc(mq & ltm) < need;
+                                cnt[q] += __popc(mq);
+                                const unsigned mh = __reduce_max_sync(FULL, mine ? hi : 0u);
+                                const unsigned ml = __reduce_max_sync(FULL, (mine && hi == mh) ? lo : 0u);
+                                if (lane == q && (mh > bh || (mh == bh && ml > bl))) { bh = mh; bl = ml; }
+                            }
+                        }
                     }
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        if (lane == q && cnt[q] >= need) mytau = __hiloint2double((int)bh, (int)bl);
                 }
                 if (lane < 8) tau[lane] = mytau;
                 __syncwarp();
@@ -687,7 +707,11 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 }
             }
             __syncwarp();
-            K = prune_list(P, nc, keys, slots, K, lane);
+            nhint = K < 64 ? K : 64;
+#ifdef K3D_DEBUG_K
+            tested = K; // debug: report the list length instead of the candidates tested
+#endif
+            K = prune_list(P, nc, keys, slots, K, lane, hint);
             na = K < P.ndmax ? K : P.ndmax; // krige3d.py:356-375
             __syncwarp();
             if (out.nbr_idx) {
@@ -766,7 +790,6 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 const int row = k / P.ndb, j = k - row * P.ndb;
                 ut[row * ucols + ndp + j] = unode[row] + udb[row * P.ndb + j];
             }
-            nhint = na;
             __syncwarp();
 
             // publish this warp's covariance job for the pooled phase
@@ -1059,7 +1082,7 @@ int make_cfg(const K3dParams *p, double mean_cand, int smem_max, KCfg *c)
     const int amax = amax_for(c->rtot);
     c->urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c->rtot;
     c->reuse = amax > 0 ? 1 : 0;
-    int want = roundup32((int)(2.5 * mean_cand) + 64);
+    int want = roundup32((int)(2.0 * mean_cand) + 64);
     if (want < 256) want = 256;
     if (want > 4096) want = 4096;
     int floor_cs = roundup32((int)(1.4 * mean_cand) + 32);
@@ -1073,7 +1096,7 @@ int make_cfg(const K3dParams *p, double mean_cand, int smem_max, KCfg *c)
             c->warps = warp_options[wi];
             c->cs = 0;
             const int fixed = off_warp(*c) + c->warps * pw_bytes(*c);
-            int cs = ((budget - fixed - 64) / 28) & ~31;
+            int cs = ((budget - fixed - 64) / 28) & ~31; // 24 B coordinates + 4 B index each
             if (cs > want) cs = want;
             if (cs >= floor_cs) {
                 c->cs = cs;
