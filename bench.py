@@ -307,6 +307,7 @@ def main():
                          "kernel_ms_per_step": kern_ms / args.steps,
                          "hbm_gbs_algorithmic": nodes * 16.0 * args.steps / (kern_ms * 1e-3) / 1e9},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "launch": _native.last_launch(),
             "wall_s_timed_region": t_wall,
         }
         if e2e is not None:

@@ -448,7 +448,7 @@ __device__ __noinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
 // the fused kernel
 // ---------------------------------------------------------------------------
 template <int AMAX>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(512, 1)
 k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
                  const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
                  const __grid_constant__ KCfg cfg)
@@ -483,8 +483,8 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     int *hint = (int *)(wbase + pw_off_hint(cfg));
 
     __shared__ int s_total, s_warpsum[32];
-    __shared__ int s_job[8][6];     // per warp: npairs, npad, na, full, R, magic
-    __shared__ double s_jloc[8][3]; // per warp: node location
+    __shared__ int s_job[16][6];     // per warp: npairs, npad, na, full, R, magic
+    __shared__ double s_jloc[16][3]; // per warp: node location
 
     // ---- tile geometry: the grid nodes that fall in super block (sbx, sby, sbz) -------
     int tile = blockIdx.x;
@@ -1088,22 +1088,25 @@ int make_cfg(const K3dParams *p, double mean_cand, int smem_max, KCfg *c)
     int floor_cs = roundup32((int)(1.4 * mean_cand) + 32);
     if (floor_cs < 128) floor_cs = 128;
     if (floor_cs > want) floor_cs = want;
-    const int half = (smem_max + 1024) / 2 - 1024 - 256; // two CTAs per SM
-    static const int warp_options[] = {8, 6, 4};
-    for (int pass = 0; pass < 2; pass++) {
-        const int budget = pass == 0 ? half : smem_max - 256;
-        for (int wi = 0; wi < 3; wi++) {
-            c->warps = warp_options[wi];
-            c->cs = 0;
-            const int fixed = off_warp(*c) + c->warps * pw_bytes(*c);
-            int cs = ((budget - fixed - 64) / 28) & ~31; // 24 B coordinates + 4 B index each
-            if (cs > want) cs = want;
-            if (cs >= floor_cs) {
-                c->cs = cs;
-                c->pw_bytes = pw_bytes(*c);
-                c->smem_bytes = off_warp(*c) + c->warps * c->pw_bytes;
-                return K3D_OK;
-            }
+    // CTA shapes in order of preference: most warps per SM first (the kernel is latency
+    // bound), two CTAs per SM before one (longer walks per warp).  128 registers per thread
+    // cap an SM at 16 warps.
+    static const int shapes[][2] = {{2, 8}, {1, 16}, {1, 14}, {2, 6}, {1, 12}, {1, 10},
+                                    {2, 4}, {1, 8}, {1, 6}, {1, 4}};
+    for (unsigned i = 0; i < sizeof(shapes) / sizeof(shapes[0]); i++) {
+        const int ctas = shapes[i][0];
+        // the driver reserves 1 KB per CTA
+        const int budget = ctas == 2 ? (smem_max + 1024) / 2 - 1024 - 256 : smem_max - 256;
+        c->warps = shapes[i][1];
+        c->cs = 0;
+        const int fixed = off_warp(*c) + c->warps * pw_bytes(*c);
+        int cs = ((budget - fixed - 64) / 28) & ~31; // 24 B coordinates + 4 B index each
+        if (cs > want) cs = want;
+        if (cs >= floor_cs) {
+            c->cs = cs;
+            c->pw_bytes = pw_bytes(*c);
+            c->smem_bytes = off_warp(*c) + c->warps * c->pw_bytes;
+            return K3D_OK;
         }
     }
     return K3D_ECAPACITY;
