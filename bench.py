@@ -271,6 +271,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": total_nodes / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "breakdown_s": {k: round(v, 4) for k, v in ke.timings.items()},
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt[0]) * 1e3,
                "includes": "Krige3d(par, data).kt3d(): super-block set-up (binning, template "
                            "kernel), pinned H2D of samples/index, fused kernel, D2H of "
