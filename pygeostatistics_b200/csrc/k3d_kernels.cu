@@ -136,12 +136,54 @@ __device__ __forceinline__ double sqdist_exact(double dx, double dy, double dz,
     return s;
 }
 
+// exp(x) for x <= 0 to ~1 ulp: x = (32 k + j) ln2/32 + r, exp(x) = 2^k * 2^(j/32) * e^r with
+// |r| <= ln2/64 (degree-6 polynomial) and 2^(j/32) from a 32-entry shared-memory table.
+// About half the instructions of the library exp; no special cases are needed on this
+// domain (results below 2^-1000 are flushed to zero).
+__device__ __forceinline__ double exp_neg(double x, const double *__restrict__ tab)
+{
+    const double magic = 6755399441055744.0; // 1.5 * 2^52
+    double kd = fma(x, 46.166241308446828384, magic); // 32 / ln 2
+    const int ki = __double2loint(kd);
+    kd -= magic;
+    double r = fma(kd, -0.021660849390173098, x); // ln2/32 high part (20 trailing zero bits)
+    r = fma(kd, -2.325192846878874e-12, r);       // low part
+    double p = 1.98412698412698412698e-04;  // 1/5040
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = p * r; // e^r - 1
+    const double t = tab[ki & 31];
+    double y = fma(t, p, t);
+    const int q = ki >> 5; // floor division: j = ki & 31 >= 0
+    y = __hiloint2double(__double2hiint(y) + (q << 20), __double2loint(y));
+    return x < -690.0 ? 0.0 : y;
+}
+
+// sqrt(a) for a > 0 to ~1 ulp: hardware reciprocal-sqrt seed, one coupled Newton step and a
+// final residual correction, without the library's special-case path.
+__device__ __forceinline__ double sqrt_pos(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    const double r = fma(-h, g, 0.5); // one coupled Newton step: ~2^-40
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    g = fma(fma(-g, g, a), h, g);     // g += (a - g^2) / (2 g): full precision
+    return a < 1e-290 ? 0.0 : g;
+}
+
 // Nested covariance (krige3d.py:838-875, cova3) from the per-structure squared scaled
 // distances h2[s] = (h/a)^2 (h^2 for a power structure).  Inlined at exactly ONE call
 // site (the assembly work loop): the transcendental code is large and the instruction
 // cache is small.
 __device__ __forceinline__ double cova_from_h2(const K3dParams &P, const KPrep &Q,
-                                               const double (&h2v)[K3D_MAXNST])
+                                               const double (&h2v)[K3D_MAXNST],
+                                               const double *__restrict__ exptab)
 {
     if (h2v[0] < Q.eps0s)
         return P.maxcov;
@@ -154,13 +196,13 @@ __device__ __forceinline__ double cova_from_h2(const K3dParams &P, const KPrep &
             const int it = Q.it[s];
             if (it == 1) {
                 if (h2 < 1.0) {
-                    double hr = sqrt(h2);
+                    double hr = sqrt_pos(h2);
                     cova += c * (1.0 - hr * (1.5 - 0.5 * h2));
                 }
             } else if (it == 2) {
-                cova += c * exp(-3.0 * sqrt(h2));
+                cova += c * exp_neg(-3.0 * sqrt_pos(h2), exptab);
             } else if (it == 3) {
-                cova += c * exp(-3.0 * h2);
+                cova += c * exp_neg(-3.0 * h2, exptab);
             } else if (it == 4) {
                 cova += P.maxcov - c * pow(sqrt(h2), Q.aa[s]);
             } else {
@@ -483,6 +525,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     int *hint = (int *)(wbase + pw_off_hint(cfg));
 
     __shared__ int s_total, s_warpsum[32];
+    __shared__ double s_exptab[32]; // 2^(j/32)
     __shared__ int s_job[16][6];     // per warp: npairs, npad, na, full, R, magic
     __shared__ double s_jloc[16][3]; // per warp: node location
 
@@ -505,6 +548,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     const double cx0 = P.xmn + x0 * P.xsiz, cy0 = P.ymn + y0 * P.ysiz,
                  cz0 = P.zmn + in.nodez0[sbz] * P.zsiz;
 
+    if (tid < 32) s_exptab[tid] = exp2((double)tid * 0.03125);
     // ---- triangular index LUT: e -> (row<<8 | col), row >= col --------------
     for (int e = tid; e < cfg.ntri; e += nthreads) {
         int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
@@ -872,7 +916,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                                     h2v[st] = dx * dx + dy * dy + dz * dz;
                                 }
                             }
-                            double c = cova_from_h2(P, Q, h2v);
+                            double c = cova_from_h2(P, Q, h2v, s_exptab);
                             if (rhs && P.ndb > 1) { // krige3d.py:792-796
                                 const double dx = (jpx[p1] - s_jloc[jw][0]) - db[sub],
                                              dy = (jpy[p1] - s_jloc[jw][1]) - db[P.ndb + sub],
@@ -1068,7 +1112,7 @@ void make_prep(const K3dParams *p, KPrep *q)
 
 // Shared-memory plan: warps per CTA and stage capacity such that two CTAs share an SM
 // when possible.  `mean_cand` is the expected number of candidate samples per tile.
-int make_cfg(const K3dParams *p, double mean_cand, int smem_max, KCfg *c)
+int make_cfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_max, KCfg *c)
 {
     memset(c, 0, sizeof(*c));
     c->rtot = p->ndmax + p->mdt + 2;
@@ -1088,26 +1132,37 @@ int make_cfg(const K3dParams *p, double mean_cand, int smem_max, KCfg *c)
     int floor_cs = roundup32((int)(1.4 * mean_cand) + 32);
     if (floor_cs < 128) floor_cs = 128;
     if (floor_cs > want) floor_cs = want;
-    // CTA shapes in order of preference: most warps per SM first (the kernel is latency
-    // bound), two CTAs per SM before one (longer walks per warp).  128 registers per thread
-    // cap an SM at 16 warps.
+    // CTA shapes (CTAs per SM, warps per CTA).  The kernel is latency bound, so more warps
+    // per SM help, but every warp starts its walk with a full-cost node (no bounds, no
+    // covariance reuse), so short walks hurt: score = warps per SM * per / (per + 4) with
+    // per = nodes per warp and tile.  128 registers per thread cap an SM at 16 warps.
     static const int shapes[][2] = {{2, 8}, {1, 16}, {1, 14}, {2, 6}, {1, 12}, {1, 10},
                                     {2, 4}, {1, 8}, {1, 6}, {1, 4}};
+    double best = -1.0;
+    KCfg pick = *c;
     for (unsigned i = 0; i < sizeof(shapes) / sizeof(shapes[0]); i++) {
         const int ctas = shapes[i][0];
-        // the driver reserves 1 KB per CTA
-        const int budget = ctas == 2 ? (smem_max + 1024) / 2 - 1024 - 256 : smem_max - 256;
+        // the driver reserves 1 KB per CTA; 1.5 KB covers the kernel's static shared memory
+        const int budget = ctas == 2 ? (smem_max + 1024) / 2 - 1024 - 1536 : smem_max - 1536;
         c->warps = shapes[i][1];
         c->cs = 0;
         const int fixed = off_warp(*c) + c->warps * pw_bytes(*c);
         int cs = ((budget - fixed - 64) / 28) & ~31; // 24 B coordinates + 4 B index each
         if (cs > want) cs = want;
-        if (cs >= floor_cs) {
+        if (cs < floor_cs) continue;
+        const double per = tile_nodes / c->warps;
+        const double score = ctas * c->warps * per / (per + 4.0);
+        if (score > best) {
+            best = score;
             c->cs = cs;
             c->pw_bytes = pw_bytes(*c);
             c->smem_bytes = off_warp(*c) + c->warps * c->pw_bytes;
-            return K3D_OK;
+            pick = *c;
         }
+    }
+    if (best > 0.0) {
+        *c = pick;
+        return K3D_OK;
     }
     return K3D_ECAPACITY;
 }
@@ -1179,7 +1234,8 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
     const double nsb = (double)p->nxsup * p->nysup * p->nzsup;
     const double mean_cand = in->ntmpl > 0 ? (double)in->nd / nsb * in->ntmpl : 512.0;
     KCfg c;
-    if (make_cfg(p, mean_cand, smem_max, &c) != K3D_OK)
+    const double tile_nodes = (double)p->nx * p->ny * p->nz / nsb;
+    if (make_cfg(p, mean_cand, tile_nodes, smem_max, &c) != K3D_OK)
         return fail(K3D_ECAPACITY, "ndmax/drift/discretisation exceed the shared memory of an SM");
     // one CTA per super block; CTAs whose super block does not meet the slab exit at once
     long long ntiles = (long long)p->nxsup * p->nysup * p->nzsup;
