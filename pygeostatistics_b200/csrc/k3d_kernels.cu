@@ -392,8 +392,8 @@ struct NodeCtx {
 // noct == 0 -> the ndmax nearest; noct > 0 -> per-octant nearest noct, at most 8*noct.
 // When `hint` is given, the (up to 64) nearest candidates are copied there in distance
 // order before the octant rule thins them: they seed the next node's bounds.
-__device__ __noinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, double *keys,
-                                       int *slots, int K, int lane, int *hint = nullptr)
+__device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, double *keys,
+                                          int *slots, int K, int lane, int *hint = nullptr)
 {
     if (K > 1) {
         int n = 32;
@@ -444,10 +444,18 @@ __device__ __noinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, do
     return kept;
 }
 
+// out-of-line copy for the rare mid-scan overflow (hot call sites inline prune_list so that
+// the list stays addressed as shared memory and the parameters as constants)
+__device__ __noinline__ int prune_list_cold(const K3dParams &P, const NodeCtx &nc, double *keys,
+                                            int *slots, int K, int lane, int *hint = nullptr)
+{
+    return prune_list(P, nc, keys, slots, K, lane, hint);
+}
+
 // Scan `count` contiguous candidates (slots slot0..slot0+count) and append those within
 // the search radius -- and within the caller's exact per-octant upper bounds tau[] --
 // to the warp's list; prunes when the list could overflow.
-__device__ __noinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
+__device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
                                                const NodeCtx &nc, int slot0, int count,
                                                const double *tau, double *keys, int *slots,
                                                int K, int lane)
@@ -474,7 +482,7 @@ __device__ __noinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
             continue;
         if (K + 32 > cfg.kcap) {
             __syncwarp();
-            K = prune_list(P, nc, keys, slots, K, lane);
+            K = prune_list_cold(P, nc, keys, slots, K, lane);
         }
         if (in) {
             int pos = K + __popc(m & lt);
@@ -484,6 +492,14 @@ __device__ __noinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
         K += __popc(m);
     }
     return K;
+}
+// out-of-line copy for the global-memory fallback walk
+__device__ __noinline__ int scan_candidates_cold(const K3dParams &P, const KCfg &cfg,
+                                                 const NodeCtx &nc, int slot0, int count,
+                                                 const double *tau, double *keys, int *slots,
+                                                 int K, int lane)
+{
+    return scan_candidates(P, cfg, nc, slot0, count, tau, keys, slots, K, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -734,7 +750,9 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             int K = 0;
             if (staged) {
                 tested = ncand;
-                K = scan_candidates(P, cfg, nc, 0, ncand, tau, keys, slots, K, lane);
+                NodeCtx ns = nc; // staged coordinates: plain shared-memory pointers
+                ns.qx = stx; ns.qy = sty; ns.qz = stz;
+                K = scan_candidates(P, cfg, ns, 0, ncand, tau, keys, slots, K, lane);
             } else { // tile too dense for the stage: walk the runs in global memory
                 for (int r = 0; r < in.nruns; r++) {
                     const int16_t *rn = in.runs + 4 * r;
@@ -746,7 +764,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     if (bx0 > bx1) continue;
                     int b = (bz * P.nysup + by) * P.nxsup;
                     int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
-                    K = scan_candidates(P, cfg, nc, lo, hi - lo, tau, keys, slots, K, lane);
+                    K = scan_candidates_cold(P, cfg, nc, lo, hi - lo, tau, keys, slots, K, lane);
                     tested += hi - lo;
                 }
             }
@@ -755,7 +773,13 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
 #ifdef K3D_DEBUG_K
             tested = K; // debug: report the list length instead of the candidates tested
 #endif
-            K = prune_list(P, nc, keys, slots, K, lane, hint);
+            if (staged) {
+                NodeCtx ns = nc;
+                ns.qx = stx; ns.qy = sty; ns.qz = stz;
+                K = prune_list(P, ns, keys, slots, K, lane, hint);
+            } else {
+                K = prune_list_cold(P, nc, keys, slots, K, lane, hint);
+            }
             na = K < P.ndmax ? K : P.ndmax; // krige3d.py:356-375
             __syncwarp();
             if (out.nbr_idx) {
