@@ -32,6 +32,12 @@
 #define K3D_VERSION_STR "pygeostatistics_b200 k3d 0.1 (sm_100a)"
 #define K3D_EPS 2.220446049250313e-16 /* 7./3-4./3-1, krige3d.py:795,853 */
 #define FULL 0xffffffffu
+#ifndef K3D_SMALL_CTAS
+#define K3D_SMALL_CTAS 3 /* resident CTAs targeted by the small-system (<= 20 rows) kernel */
+#endif
+#ifndef K3D_NHINT
+#define K3D_NHINT 32 /* previous-node candidates re-measured for the search bounds (<= 64) */
+#endif
 // The warps of a CTA move through the phases of a node together (search+fill /
 // covariances / solve): warps that run the same loop share instruction-cache lines, which
 // measured as the difference between 2.5 and 0.2 "no instruction" stall cycles per issue.
@@ -506,7 +512,7 @@ __device__ __noinline__ int scan_candidates_cold(const K3dParams &P, const KCfg 
 // the fused kernel
 // ---------------------------------------------------------------------------
 template <int AMAX>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(AMAX == 5 ? 256 : 512, AMAX == 5 ? K3D_SMALL_CTAS : 1)
 k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
                  const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
                  const __grid_constant__ KCfg cfg)
@@ -769,7 +775,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 }
             }
             __syncwarp();
-            nhint = K < 64 ? K : 64;
+            nhint = K < K3D_NHINT ? K : K3D_NHINT;
 #ifdef K3D_DEBUG_K
             tested = K; // debug: report the list length instead of the candidates tested
 #endif
