@@ -1144,6 +1144,8 @@ void make_prep(const K3dParams *p, KPrep *q)
 // when possible.  `mean_cand` is the expected number of candidate samples per tile.
 int make_cfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_max, KCfg *c)
 {
+    // the small-system kernel is compiled for CTAs of at most 8 warps
+    const int max_warps = amax_for(p->ndmax + p->mdt + 2) == 5 ? 8 : 16;
     memset(c, 0, sizeof(*c));
     c->rtot = p->ndmax + p->mdt + 2;
     c->ntri = c->rtot * (c->rtot + 1) / 2;
@@ -1175,6 +1177,7 @@ int make_cfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_m
         // the driver reserves 1 KB per CTA; 1.5 KB covers the kernel's static shared memory
         const int budget = ctas == 2 ? (smem_max + 1024) / 2 - 1024 - 1536 : smem_max - 1536;
         c->warps = shapes[i][1];
+        if (c->warps > max_warps) continue;
         c->cs = 0;
         const int fixed = off_warp(*c) + c->warps * pw_bytes(*c);
         int cs = ((budget - fixed - 64) / 28) & ~31; // 24 B coordinates + 4 B index each

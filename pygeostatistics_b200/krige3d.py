@@ -17,6 +17,7 @@ octant search (`noct`), block kriging (`nxdis/nydis/nzdis`), `itrend`, and the g
 output file (`outfl`, via write_output()).
 """
 import ctypes as C
+import sys
 import time
 from collections import namedtuple
 
@@ -29,19 +30,22 @@ from .super_block import SuperBlockSearcher
 
 EPS = np.finfo(float).eps
 
-_PINNED = {}
+_PINNED = []
 
 
-def _pinned(name, numel, dtype):
-    """Page-locked host buffers for the result copies, kept between calls (pinning
-    hundreds of MB costs tens of ms; device->host copies into pageable memory run at a
-    fraction of the PCIe rate)."""
-    key = (name, dtype)
-    buf = _PINNED.get(key)
-    if buf is None or buf.numel() < numel:
-        buf = torch.empty(max(numel, 1), dtype=dtype, pin_memory=True)
-        _PINNED[key] = buf
-    return buf[:numel]
+def _pinned(numel, dtype):
+    """Page-locked host buffer for a result copy.  Buffers are pooled: pinning (and first
+    touching) hundreds of MB costs ~100 ms, several times the PCIe copy itself.  A pooled
+    buffer is handed out again only when nothing references it any more -- the numpy
+    arrays given to the caller keep their buffer alive and private."""
+    for buf in _PINNED:
+        if buf.dtype == dtype and buf.numel() >= numel and sys.getrefcount(buf) <= 3:
+            return buf
+    buf = torch.empty(max(numel, 1), dtype=dtype, pin_memory=True)
+    _PINNED.append(buf)
+    if len(_PINNED) > 16:
+        _PINNED[:] = [b_ for b_ in _PINNED if sys.getrefcount(b_) > 3][-15:] + [buf]
+    return buf
 
 
 def slab_ranges(nz, world_size):
@@ -481,12 +485,12 @@ class Krige3d(object):
                    for k, v in out.items()}
         res = {}
         for k, v in out.items():
-            res[k] = _pinned(k, v.numel(), v.dtype)
+            buf = _pinned(v.numel(), v.dtype)
+            res[k] = buf[:v.numel()]   # a view: keeps `buf` referenced while in use
             res[k].copy_(v, non_blocking=True)
+            del buf
         torch.cuda.synchronize(self._device())
         self.timings['krige_s'] = time.time() - t0
-        # the pinned buffers are reused by the next call: hand out private copies
-        res = {k: v.clone() for k, v in res.items()}
         self.timings['total_s'] = time.time() - t0 + self.timings.get('setup_s', 0.0)
         self.estimation = res['est'].numpy()
         self.estimation_variance = res['var'].numpy()
