@@ -17,8 +17,8 @@ octant search (`noct`), block kriging (`nxdis/nydis/nzdis`), `itrend`, and the g
 output file (`outfl`, via write_output()).
 """
 import ctypes as C
-import sys
 import time
+import weakref
 from collections import namedtuple
 
 import numpy as np
@@ -30,22 +30,30 @@ from .super_block import SuperBlockSearcher
 
 EPS = np.finfo(float).eps
 
-_PINNED = []
+_PINNED = []  # [pinned tensor, weakref to the ndarray it was lent to (or None)]
 
 
-def _pinned(numel, dtype):
-    """Page-locked host buffer for a result copy.  Buffers are pooled: pinning (and first
-    touching) hundreds of MB costs ~100 ms, several times the PCIe copy itself.  A pooled
-    buffer is handed out again only when nothing references it any more -- the numpy
-    arrays given to the caller keep their buffer alive and private."""
-    for buf in _PINNED:
-        if buf.dtype == dtype and buf.numel() >= numel and sys.getrefcount(buf) <= 3:
-            return buf
-    buf = torch.empty(max(numel, 1), dtype=dtype, pin_memory=True)
-    _PINNED.append(buf)
-    if len(_PINNED) > 16:
-        _PINNED[:] = [b_ for b_ in _PINNED if sys.getrefcount(b_) > 3][-15:] + [buf]
-    return buf
+def _pinned_array(numel, dtype):
+    """Page-locked host buffer for a result copy, as (tensor view, ndarray view).  Buffers
+    are pooled: pinning (and first touching) hundreds of MB costs ~100 ms, several times
+    the PCIe copy itself.  A buffer is lent out again only after the ndarray it backed has
+    been garbage collected, so the arrays handed to the caller stay private."""
+    entry = None
+    for e in _PINNED:
+        if e[0].dtype == dtype and e[0].numel() >= numel and (e[1] is None or e[1]() is None):
+            entry = e
+            break
+    if entry is None:
+        entry = [torch.empty(max(numel, 1), dtype=dtype, pin_memory=True), None]
+        _PINNED.append(entry)
+        if len(_PINNED) > 16:  # drop idle buffers, oldest first
+            idle = [e for e in _PINNED[:-1] if e[1] is None or e[1]() is None]
+            for e in idle[:len(_PINNED) - 16]:
+                _PINNED.remove(e)
+    view = entry[0][:numel]
+    arr = view.numpy()
+    entry[1] = weakref.ref(arr)
+    return view, arr
 
 
 def slab_ranges(nz, world_size):
@@ -485,20 +493,19 @@ class Krige3d(object):
                    for k, v in out.items()}
         res = {}
         for k, v in out.items():
-            buf = _pinned(v.numel(), v.dtype)
-            res[k] = buf[:v.numel()]   # a view: keeps `buf` referenced while in use
-            res[k].copy_(v, non_blocking=True)
-            del buf
+            view, arr = _pinned_array(v.numel(), v.dtype)
+            view.copy_(v, non_blocking=True)
+            res[k] = arr
         torch.cuda.synchronize(self._device())
         self.timings['krige_s'] = time.time() - t0
         self.timings['total_s'] = time.time() - t0 + self.timings.get('setup_s', 0.0)
-        self.estimation = res['est'].numpy()
-        self.estimation_variance = res['var'].numpy()
-        self.status = res['status'].numpy()
+        self.estimation = res['est']
+        self.estimation_variance = res['var']
+        self.status = res['status']
         if neighbours:
-            idx = res['nbr_idx'].numpy().reshape(-1, self.ndmax).astype(np.int64)
-            self.neighbour_count = res['nbr_cnt'].numpy()
-            self.candidates_tested = res['ncand'].numpy()
+            idx = res['nbr_idx'].reshape(-1, self.ndmax).astype(np.int64)
+            self.neighbour_count = res['nbr_cnt']
+            self.candidates_tested = res['ncand']
             orig = np.where(idx >= 0, self.searcher.sort_index[np.maximum(idx, 0)], -1)
             self.neighbours = orig
             self.neighbours_sorted_space = idx

@@ -199,3 +199,27 @@ def test_two_rank_z_slab_sharding_gloo(tmp_path):
                           str(port), str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GATHER_OK" in out.stdout
+
+
+def test_pinned_result_pool_keeps_arrays_private(monkeypatch):
+    """Result buffers are pooled page-locked memory; a buffer may only be lent again after
+    the ndarray it backed is gone (a second Krige3d must not overwrite the first's results)."""
+    import gc
+    import torch
+    import pygeostatistics_b200.krige3d as k3
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **kw: real_empty(
+        *a, **{k: v for k, v in kw.items() if k != "pin_memory"}))
+    monkeypatch.setattr(k3, "_PINNED", [])
+    _, a1 = k3._pinned_array(10, torch.float64)
+    a1[:] = 1.0
+    _, a2 = k3._pinned_array(10, torch.float64)
+    a2[:] = 2.0
+    assert a1[0] == 1.0 and a2[0] == 2.0 and len(k3._PINNED) == 2
+    del a1
+    gc.collect()
+    _, a3 = k3._pinned_array(8, torch.float64)      # reuses the freed buffer
+    a3[:] = 3.0
+    assert len(k3._PINNED) == 2 and a2[0] == 2.0
+    _, a4 = k3._pinned_array(8, torch.uint8)        # other dtype: its own buffer
+    assert len(k3._PINNED) == 3 and a4.dtype == np.uint8
