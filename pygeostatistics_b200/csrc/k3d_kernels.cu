@@ -36,7 +36,7 @@
 #define K3D_SMALL_CTAS 3 /* resident CTAs targeted by the small-system (<= 20 rows) kernel */
 #endif
 #ifndef K3D_NHINT
-#define K3D_NHINT 32 /* previous-node candidates re-measured for the search bounds (<= 64) */
+#define K3D_NHINT 32 /* previous node's neighbours re-measured for the search bounds (<= 32) */
 #endif
 // The warps of a CTA move through the phases of a node together (search+fill /
 // covariances / solve): warps that run the same loop share instruction-cache lines, which
@@ -103,7 +103,9 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 //                                             the node's block points (columns ndp..)
 //         [pslot,pid,newpos,newslot i32 x ndp] staged slot / sample id / fill list
 //         [pivot rows f64 x 2*urow][tau f64 x 8][unode f64 x 3*nst]
-//         [hint i32 x 64]                     previous node's nearest candidates (slots)
+//         [hint i32 x 32]                     previous node's neighbours (slots)
+//         [octs u8 x kcap]                    octant of every listed candidate
+//         [sub u16 x cs/2]                    staged candidates that can matter to the walk
 __host__ __device__ inline int off_tri(const KCfg &) { return 0; }
 __host__ __device__ inline int off_stage(const KCfg &c) { return align16(c.ntri * 2); }
 __host__ __device__ inline int off_sidx(const KCfg &c) { return off_stage(c) + c.cs * 24; }
@@ -120,7 +122,7 @@ __host__ __device__ inline int pw_off_tau(const KCfg &c) { return pw_off_rows(c)
 __host__ __device__ inline int pw_off_hint(const KCfg &c) { return pw_off_tau(c) + (8 + 3 * c.nst) * 8; }
 __host__ __device__ inline int pw_bytes(const KCfg &c)
 {
-    return align16(pw_off_hint(c) + 64 * 4);
+    return align16(pw_off_hint(c) + 32 * 4 + c.kcap + (c.cs >> 1) * 2);
 }
 
 // ---------------------------------------------------------------------------
@@ -396,10 +398,8 @@ struct NodeCtx {
 
 // Sort the K collected candidates and keep what the reference would keep:
 // noct == 0 -> the ndmax nearest; noct > 0 -> per-octant nearest noct, at most 8*noct.
-// When `hint` is given, the (up to 64) nearest candidates are copied there in distance
-// order before the octant rule thins them: they seed the next node's bounds.
 __device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, double *keys,
-                                          int *slots, int K, int lane, int *hint = nullptr)
+                                          int *slots, int K, int lane)
 {
     if (K > 1) {
         int n = 32;
@@ -410,10 +410,6 @@ __device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc,
         }
         __syncwarp();
         warp_bitonic(keys, slots, n, lane);
-    }
-    if (hint) {
-        const int nh = K < 64 ? K : 64;
-        for (int t = lane; t < nh; t += 32) hint[t] = slots[t];
     }
     if (P.noct <= 0)
         return K < P.ndmax ? K : P.ndmax;
@@ -453,9 +449,55 @@ __device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc,
 // out-of-line copy for the rare mid-scan overflow (hot call sites inline prune_list so that
 // the list stays addressed as shared memory and the parameters as constants)
 __device__ __noinline__ int prune_list_cold(const K3dParams &P, const NodeCtx &nc, double *keys,
-                                            int *slots, int K, int lane, int *hint = nullptr)
+                                            int *slots, int K, int lane)
 {
-    return prune_list(P, nc, keys, slots, K, lane, hint);
+    return prune_list(P, nc, keys, slots, K, lane);
+}
+
+// Selection for short lists (K <= 64, the usual case once the bounds of the previous node
+// apply): instead of sorting, the surplus is removed -- per octant the farthest candidates
+// beyond noct, then the farthest overall beyond ndmax -- one warp-wide lexicographic
+// maximum of (distance bits, slot) per removal.  Leaves the kept candidates, unordered,
+// at the front of the list; which ones are kept is exactly what the sort + octant pass keeps.
+__device__ __forceinline__ int select_small(const K3dParams &P, double *keys, int *slots,
+                                            const unsigned char *octs, int K, int lane)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    bool v0 = lane < K, v1 = lane + 32 < K;
+    const double k0 = v0 ? keys[lane] : 0.0, k1 = v1 ? keys[lane + 32] : 0.0;
+    const unsigned hi0 = (unsigned)__double2hiint(k0), lo0 = (unsigned)__double2loint(k0);
+    const unsigned hi1 = (unsigned)__double2hiint(k1), lo1 = (unsigned)__double2loint(k1);
+    const int s0 = v0 ? slots[lane] : 0, s1 = v1 ? slots[lane + 32] : 0;
+    const int o0 = v0 ? octs[lane] : 8, o1 = v1 ? octs[lane + 32] : 8;
+    // removes the lexicographically largest element among those flagged a0 / a1
+    auto remove_max = [&](bool a0, bool a1) {
+        const bool use1 = a1 && (!a0 || hi1 > hi0 || (hi1 == hi0 && (lo1 > lo0 || (lo1 == lo0 && s1 > s0))));
+        const bool any = a0 || a1;
+        const unsigned ch = any ? (use1 ? hi1 : hi0) : 0u;
+        const unsigned mh = __reduce_max_sync(FULL, ch);
+        const unsigned cl = (any && ch == mh) ? (use1 ? lo1 : lo0) : 0u;
+        const unsigned ml = __reduce_max_sync(FULL, cl);
+        const unsigned cs = (any && ch == mh && cl == ml) ? (unsigned)(use1 ? s1 : s0) + 1u : 0u;
+        const unsigned ms = __reduce_max_sync(FULL, cs);
+        if (cs == ms && cs != 0u) {
+            if (use1) v1 = false; else v0 = false;
+        }
+    };
+    if (P.noct > 0) {
+        for (int o = 0; o < 8; o++) {
+            int c = __popc(__ballot_sync(FULL, v0 && o0 == o)) + __popc(__ballot_sync(FULL, v1 && o1 == o));
+            for (; c > P.noct; c--) remove_max(v0 && o0 == o, v1 && o1 == o);
+        }
+    }
+    int total = __popc(__ballot_sync(FULL, v0)) + __popc(__ballot_sync(FULL, v1));
+    for (; total > P.ndmax; total--) remove_max(v0, v1);
+    // compact the survivors to the front (all lanes hold their elements in registers)
+    const unsigned m0 = __ballot_sync(FULL, v0), m1 = __ballot_sync(FULL, v1);
+    __syncwarp();
+    if (v0) { const int p = __popc(m0 & lt); keys[p] = k0; slots[p] = s0; }
+    if (v1) { const int p = __popc(m0) + __popc(m1 & lt); keys[p] = k1; slots[p] = s1; }
+    __syncwarp();
+    return total;
 }
 
 // Scan `count` contiguous candidates (slots slot0..slot0+count) and append those within
@@ -464,7 +506,8 @@ __device__ __noinline__ int prune_list_cold(const K3dParams &P, const NodeCtx &n
 __device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
                                                const NodeCtx &nc, int slot0, int count,
                                                const double *tau, double *keys, int *slots,
-                                               int K, int lane)
+                                               unsigned char *octs, int K, int lane,
+                                               const unsigned short *sub = nullptr)
 {
     const double *rs = P.rotmat + 9 * P.nst;
     const unsigned lt = (1u << lane) - 1u;
@@ -472,28 +515,36 @@ __device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &c
         int c = base + lane;
         bool in = false;
         double h = 0.0;
+        int oq = 0, s = 0;
         if (c < count) {
-            int s = slot0 + c;
+            s = sub ? (int)sub[c] : slot0 + c; // candidates come from the walk's short list
             // point1 = node, point2 = sample (super_block.py:301-305)
             double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
                    dz = __dsub_rn(nc.zloc, nc.qz[s]);
             h = sqdist_exact(dx, dy, dz, rs);
             // reference: `if hsqd > radsqd: continue`; tau[] <= radsqd are exact upper
             // bounds of what can still be selected in the sample's octant
-            double bound = tau[P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0];
-            in = !(h > bound);
+            oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
+            in = !(h > tau[oq]);
         }
         unsigned m = __ballot_sync(FULL, in);
         if (m == 0u)
             continue;
-        if (K + 32 > cfg.kcap) {
+        if (K + 32 > cfg.kcap) { // rare: thin the list (sorted afterwards); re-derive octants
             __syncwarp();
             K = prune_list_cold(P, nc, keys, slots, K, lane);
+            for (int t = lane; t < K; t += 32) {
+                const int sl = slots[t];
+                octs[t] = (unsigned char)(P.noct > 0 ? octant_of_neg(nc.xloc - nc.qx[sl], nc.yloc - nc.qy[sl],
+                                                                      nc.zloc - nc.qz[sl]) : 0);
+            }
+            __syncwarp();
         }
         if (in) {
             int pos = K + __popc(m & lt);
             keys[pos] = h;
-            slots[pos] = slot0 + c;
+            slots[pos] = s;
+            octs[pos] = (unsigned char)oq;
         }
         K += __popc(m);
     }
@@ -503,9 +554,9 @@ __device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &c
 __device__ __noinline__ int scan_candidates_cold(const K3dParams &P, const KCfg &cfg,
                                                  const NodeCtx &nc, int slot0, int count,
                                                  const double *tau, double *keys, int *slots,
-                                                 int K, int lane)
+                                                 unsigned char *octs, int K, int lane)
 {
-    return scan_candidates(P, cfg, nc, slot0, count, tau, keys, slots, K, lane);
+    return scan_candidates(P, cfg, nc, slot0, count, tau, keys, slots, octs, K, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -545,6 +596,8 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     double *tau = (double *)(wbase + pw_off_tau(cfg));
     double *unode = tau + 8;
     int *hint = (int *)(wbase + pw_off_hint(cfg));
+    unsigned char *octs = (unsigned char *)(hint + 32);
+    unsigned short *sub = (unsigned short *)(octs + cfg.kcap);
 
     __shared__ int s_total, s_warpsum[32];
     __shared__ double s_exptab[32]; // 2^(j/32)
@@ -674,6 +727,55 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     int nprev = -1; // neighbours of the previous node whose covariances are still in Pm
     int nhint = -1; // previous node's nearest candidates listed in hint[]
 
+    // ---- candidates that can matter to this walk ------------------------------------------
+    // A sample farther from the centre of the walk's bounding box than radius + rho (rho =
+    // the box's half diagonal in the search metric) is out of range of every node of the
+    // walk (triangle inequality), so the per-node scans only visit the others.
+    int nsubw = -1; // length of sub[], or -1: scan every staged candidate
+    if (staged && t_begin < t_end) {
+        int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
+        for (int t = t_begin + lane; t < t_end; t += 32) {
+            const int lz = t / (tnx * tny), rem = t - lz * (tnx * tny);
+            const int lyr = rem / tnx, lxr = rem - lyr * tnx;
+            const int ly = (lz & 1) ? tny - 1 - lyr : lyr;
+            const int lx = ((lz * tny + lyr) & 1) ? tnx - 1 - lxr : lxr;
+            lo[0] = min(lo[0], lx); hi[0] = max(hi[0], lx);
+            lo[1] = min(lo[1], ly); hi[1] = max(hi[1], ly);
+            lo[2] = min(lo[2], lz); hi[2] = max(hi[2], lz);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[k] = __reduce_min_sync(FULL, lo[k]);
+            hi[k] = __reduce_max_sync(FULL, hi[k]);
+        }
+        const double bcx = P.xmn + (x0 + 0.5 * (lo[0] + hi[0])) * P.xsiz,
+                     bcy = P.ymn + (y0 + 0.5 * (lo[1] + hi[1])) * P.ysiz,
+                     bcz = P.zmn + (z0 + 0.5 * (lo[2] + hi[2])) * P.zsiz;
+        const double ex = 0.5 * (hi[0] - lo[0]) * fabs(P.xsiz), ey = 0.5 * (hi[1] - lo[1]) * fabs(P.ysiz),
+                     ez = 0.5 * (hi[2] - lo[2]) * fabs(P.zsiz);
+        const double *rs = P.rotmat + 9 * P.nst;
+        double rho2 = 0.0; // corners come in +- pairs: four sign patterns suffice
+        rho2 = fmax(rho2, sqdist_exact(ex, ey, ez, rs));
+        rho2 = fmax(rho2, sqdist_exact(ex, ey, -ez, rs));
+        rho2 = fmax(rho2, sqdist_exact(ex, -ey, ez, rs));
+        rho2 = fmax(rho2, sqdist_exact(ex, -ey, -ez, rs));
+        const double reach = (sqrt(P.radsqd) + sqrt(rho2)) * (1.0 + 1e-9);
+        const double reach2 = reach * reach;
+        const int subcap = cfg.cs >> 1;
+        int n = 0;
+        for (int base = 0; base < ncand; base += 32) {
+            const int c = base + lane;
+            bool near = false;
+            if (c < ncand) near = !(sqdist_exact(bcx - stx[c], bcy - sty[c], bcz - stz[c], rs) > reach2);
+            const unsigned m = __ballot_sync(FULL, near);
+            if (n + 32 > subcap) { n = -1; break; } // does not fit: keep the full scan
+            if (near) sub[n + __popc(m & ltm)] = (unsigned short)c;
+            n += __popc(m);
+        }
+        nsubw = n;
+        __syncwarp();
+    }
+
     for (int tt = 0; tt < per; tt++) {
         const int t = t_begin + tt;
         const bool active = t < t_end;
@@ -755,10 +857,15 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             // ---- 1. neighbour search ------------------------------------------
             int K = 0;
             if (staged) {
-                tested = ncand;
                 NodeCtx ns = nc; // staged coordinates: plain shared-memory pointers
                 ns.qx = stx; ns.qy = sty; ns.qz = stz;
-                K = scan_candidates(P, cfg, ns, 0, ncand, tau, keys, slots, K, lane);
+                if (nsubw >= 0) {
+                    tested = nsubw;
+                    K = scan_candidates(P, cfg, ns, 0, nsubw, tau, keys, slots, octs, K, lane, sub);
+                } else {
+                    tested = ncand;
+                    K = scan_candidates(P, cfg, ns, 0, ncand, tau, keys, slots, octs, K, lane);
+                }
             } else { // tile too dense for the stage: walk the runs in global memory
                 for (int r = 0; r < in.nruns; r++) {
                     const int16_t *rn = in.runs + 4 * r;
@@ -770,22 +877,32 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     if (bx0 > bx1) continue;
                     int b = (bz * P.nysup + by) * P.nxsup;
                     int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
-                    K = scan_candidates_cold(P, cfg, nc, lo, hi - lo, tau, keys, slots, K, lane);
+                    K = scan_candidates_cold(P, cfg, nc, lo, hi - lo, tau, keys, slots, octs, K, lane);
                     tested += hi - lo;
                 }
             }
             __syncwarp();
-            nhint = K < K3D_NHINT ? K : K3D_NHINT;
-#ifdef K3D_DEBUG_K
-            tested = K; // debug: report the list length instead of the candidates tested
-#endif
-            if (staged) {
+            // select: which candidates the reference keeps (super_block.py:313-316 + octants)
+            if (K <= 64) {
+                K = select_small(P, keys, slots, octs, K, lane);
+                if (out.nbr_idx && K > 1) { // reported lists are ordered by (distance, index)
+                    const int n = K <= 32 ? 32 : 64;
+                    for (int t = K + lane; t < n; t += 32) {
+                        keys[t] = __longlong_as_double(0x7ff0000000000000LL);
+                        slots[t] = 0x7fffffff;
+                    }
+                    __syncwarp();
+                    warp_bitonic(keys, slots, n, lane);
+                }
+            } else if (staged) {
                 NodeCtx ns = nc;
                 ns.qx = stx; ns.qy = sty; ns.qz = stz;
-                K = prune_list(P, ns, keys, slots, K, lane, hint);
+                K = prune_list(P, ns, keys, slots, K, lane);
             } else {
-                K = prune_list_cold(P, nc, keys, slots, K, lane, hint);
+                K = prune_list_cold(P, nc, keys, slots, K, lane);
             }
+            nhint = K < K3D_NHINT ? K : K3D_NHINT; // this node's neighbours seed the next bounds
+            if (lane < nhint) hint[lane] = slots[lane];
             na = K < P.ndmax ? K : P.ndmax; // krige3d.py:356-375
             __syncwarp();
             if (out.nbr_idx) {
@@ -916,9 +1033,14 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         int part = 0;
                         if (rhs) { // sample p1 against block points [sub0, sub0 + nsub)
                             p1 = w - jnpad;
-                            while (p1 >= jnapad) { p1 -= jnapad; part++; } // uniform per round
-                            sub0 = (part * P.ndb) / nsplit;
-                            nsub = p1 < jna ? ((part + 1) * P.ndb) / nsplit - sub0 : 0;
+                            if (nsplit > 1) {
+                                while (p1 >= jnapad) { p1 -= jnapad; part++; } // uniform per round
+                                sub0 = (part * P.ndb) / nsplit;
+                                nsub = ((part + 1) * P.ndb) / nsplit - sub0;
+                            } else {
+                                nsub = P.ndb;
+                            }
+                            if (p1 >= jna) nsub = 0;
                             p2 = ndp + sub0;
                         } else if (w < jnpairs) {
                             if (jfull) {
@@ -1180,7 +1302,8 @@ int make_cfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_m
         if (c->warps > max_warps) continue;
         c->cs = 0;
         const int fixed = off_warp(*c) + c->warps * pw_bytes(*c);
-        int cs = ((budget - fixed - 64) / 28) & ~31; // 24 B coordinates + 4 B index each
+        // per candidate: 24 B coordinates + 4 B index in the stage, 1 B of short list per warp
+        int cs = ((budget - fixed - 64) / (28 + c->warps)) & ~31;
         if (cs > want) cs = want;
         if (cs < floor_cs) continue;
         const double per = tile_nodes / c->warps;

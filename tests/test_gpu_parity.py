@@ -243,7 +243,7 @@ def test_file_based_drop_in(tmp_path):
     parsed = SpatialData(k.datafl).vr
     from pygeostatistics_b200.gslib_io import read_grid_column
     k_mem = gpu_run(par, {n: parsed[n] for n in ('x', 'y', 'z', 'v', 'sec')},
-                    read_grid_column(k.extfl, k.iextve))
+                    read_grid_column(k.extfl, k.iextve), neighbours=False)
     assert np.array_equal(k.estimation, k_mem.estimation, equal_nan=True)
     # ... and to the original columns up to the text round trip (the reference's
     # pd.read_csv call uses pandas' fast float parser, which is not correctly rounded)
