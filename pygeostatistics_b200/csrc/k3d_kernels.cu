@@ -1291,13 +1291,15 @@ int make_cfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_m
     // covariance reuse), so short walks hurt: score = warps per SM * per / (per + 4) with
     // per = nodes per warp and tile.  128 registers per thread cap an SM at 16 warps.
     static const int shapes[][2] = {{2, 8}, {1, 16}, {1, 14}, {2, 6}, {1, 12}, {1, 10},
-                                    {2, 4}, {1, 8}, {1, 6}, {1, 4}};
+                                    {2, 4}, {1, 8}, {1, 6}, {1, 4},
+                                    // small tiles (few nodes per super block): many small CTAs
+                                    {3, 5}, {4, 4}, {5, 3}, {8, 2}, {6, 2}, {4, 2}, {3, 4}};
     double best = -1.0;
     KCfg pick = *c;
     for (unsigned i = 0; i < sizeof(shapes) / sizeof(shapes[0]); i++) {
         const int ctas = shapes[i][0];
         // the driver reserves 1 KB per CTA; 1.5 KB covers the kernel's static shared memory
-        const int budget = ctas == 2 ? (smem_max + 1024) / 2 - 1024 - 1536 : smem_max - 1536;
+        const int budget = (smem_max + 1024) / ctas - 1024 - 1536;
         c->warps = shapes[i][1];
         if (c->warps > max_warps) continue;
         c->cs = 0;
