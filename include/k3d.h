@@ -153,10 +153,13 @@ int k3d_build_template(int32_t nxsup, int32_t nysup, int32_t nzsup, double xsizs
 int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
                         const K3dOutputs *out);
 
-/* Kernel launch facts for the last k3d_krige_slab on this thread (bench / tests). */
+/* Kernel launch facts for the last k3d_krige_slab on this thread (bench / tests).
+   `launches` counts kernels launched so far: a slab takes one search and one solve kernel
+   per run of z-planes (one run unless the neighbour scratch would exceed 2 GB). */
 typedef struct K3dLaunchInfo {
-    int32_t grid, block, smem_bytes, warps_per_cta;
+    int32_t grid, block, smem_bytes, warps_per_cta; /* solve kernel */
     int32_t stage_capacity, list_capacity, launches;
+    int32_t search_block, search_smem_bytes;        /* search kernel */
     int32_t _pad;
 } K3dLaunchInfo;
 int k3d_last_launch(K3dLaunchInfo *info);

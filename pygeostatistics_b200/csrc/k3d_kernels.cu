@@ -24,7 +24,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "k3d.h"
@@ -46,7 +48,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local K3dLaunchInfo g_launch = {0, 0, 0, 0, 0, 0, 0, 0};
+thread_local K3dLaunchInfo g_launch = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 int fail(int code, const char *fmt, const char *detail = "")
 {
@@ -64,20 +66,30 @@ int fail(int code, const char *fmt, const char *detail = "")
 // ---------------------------------------------------------------------------
 // kernel configuration (computed on the host, identical formulas on both sides)
 // ---------------------------------------------------------------------------
-struct KCfg {
+// The path runs as two kernels per slab: a SEARCH kernel (many light warps per SM) that
+// writes every node's neighbour list, and a SOLVE kernel (register-heavy warps) that turns
+// the lists into estimates.  Both work tile by tile (tile = grid nodes of one super block).
+struct SCfg {       // search kernel
     int warps;      // warps per CTA
-    int rtot;       // ndmax + mdt + 2 rows in the bordered system
-    int ntri;       // rtot*(rtot+1)/2 packed entries
-    int ndp;        // ndmax rounded up to a multiple of 4
-    int kcap;       // per-warp candidate list capacity (multiple of 32)
+    int kcap;       // per-warp candidate list capacity (power of two)
     int cs;         // staged candidate capacity per CTA
     int keepmax;    // max entries that survive a prune: noct>0 ? 8*noct : ndmax
     int pw_bytes;   // per-warp shared bytes
     int smem_bytes; // total dynamic shared bytes
+};
+struct BCfg {       // solve kernel
+    int warps;      // warps per CTA
+    int rtot;       // ndmax + mdt + 2 rows in the bordered system
+    int ntri;       // rtot*(rtot+1)/2 packed entries
+    int ndp;        // ndmax rounded up to a multiple of 4
     int nst;        // number of variogram structures
     int ndb;        // block discretisation points
     int urow;       // doubles in one pivot-row buffer (register solve) or rtot (generic)
     int reuse;      // 1: keep the sample-sample covariance block between adjacent nodes
+    int nsplit;     // block kriging: work items per sample of the right-hand side
+    int napad;      // ndmax rounded up to a multiple of 32
+    int pw_bytes;   // per-warp shared bytes
+    int smem_bytes; // total dynamic shared bytes
 };
 
 // Variogram structures prepared on the host for the kernel: the rotation matrix of
@@ -94,35 +106,42 @@ struct KPrep {
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 // shared memory carve-up (bytes from the dynamic smem base)
-//   CTA : [tri LUT u16 x ntri][stage x,y,z f64 x cs][stage idx i32 x cs]
-//         [chunk i32 x 3*threads][block points per structure f64 x 3*nst*ndb]
-//   warp: [P f64 x ntri]                      pristine bordered system (persists)
-//         [keys f64 x kcap][slots i32 x kcap] search list
-//         [px,py,pz,va,ve f64 x ndp]          neighbours by matrix position
-//         [ut f64 x 3*nst*(ndp+ndb)]          their coordinates in structure space, then
-//                                             the node's block points (columns ndp..)
-//         [pslot,pid,newpos,newslot i32 x ndp] staged slot / sample id / fill list
-//         [pivot rows f64 x 2*urow][tau f64 x 8][unode f64 x 3*nst]
-//         [hint i32 x 32]                     previous node's neighbours (slots)
-//         [octs u8 x kcap]                    octant of every listed candidate
-//         [sub u16 x cs/2]                    staged candidates that can matter to the walk
-__host__ __device__ inline int off_tri(const KCfg &) { return 0; }
-__host__ __device__ inline int off_stage(const KCfg &c) { return align16(c.ntri * 2); }
-__host__ __device__ inline int off_sidx(const KCfg &c) { return off_stage(c) + c.cs * 24; }
-__host__ __device__ inline int off_chunk(const KCfg &c) { return align16(off_sidx(c) + c.cs * 4); }
-__host__ __device__ inline int off_udb(const KCfg &c) { return align16(off_chunk(c) + c.warps * 32 * 12); }
-__host__ __device__ inline int off_warp(const KCfg &c) { return align16(off_udb(c) + 3 * c.nst * c.ndb * 8); }
-__host__ __device__ inline int pw_off_keys(const KCfg &c) { return align16(c.ntri * 8); }
-__host__ __device__ inline int pw_off_slots(const KCfg &c) { return pw_off_keys(c) + c.kcap * 8; }
-__host__ __device__ inline int pw_off_pos(const KCfg &c) { return align16(pw_off_slots(c) + c.kcap * 4); }
-__host__ __device__ inline int pw_off_ut(const KCfg &c) { return pw_off_pos(c) + 5 * c.ndp * 8; }
-__host__ __device__ inline int pw_off_ints(const KCfg &c) { return pw_off_ut(c) + 3 * c.nst * (c.ndp + c.ndb) * 8; }
-__host__ __device__ inline int pw_off_rows(const KCfg &c) { return align16(pw_off_ints(c) + 4 * c.ndp * 4); }
-__host__ __device__ inline int pw_off_tau(const KCfg &c) { return pw_off_rows(c) + 2 * c.urow * 8; }
-__host__ __device__ inline int pw_off_hint(const KCfg &c) { return pw_off_tau(c) + (8 + 3 * c.nst) * 8; }
-__host__ __device__ inline int pw_bytes(const KCfg &c)
+// search kernel
+//   CTA : [stage x,y,z f64 x cs][stage idx i32 x cs][chunk i32 x 3*threads]
+//   warp: [keys f64 x kcap][slots i32 x kcap]  candidate list
+//         [tau f64 x 8]                         per-octant bounds
+//         [hint i32 x 32]                       previous node's neighbours (slots)
+//         [octs u8 x kcap]                      octant of every listed candidate
+//         [sub u16 x cs/2]                      staged candidates that can matter to the walk
+__host__ __device__ inline int s_off_sidx(const SCfg &c) { return c.cs * 24; }
+__host__ __device__ inline int s_off_chunk(const SCfg &c) { return align16(s_off_sidx(c) + c.cs * 4); }
+__host__ __device__ inline int s_off_warp(const SCfg &c) { return align16(s_off_chunk(c) + c.warps * 32 * 12); }
+__host__ __device__ inline int spw_off_slots(const SCfg &c) { return c.kcap * 8; }
+__host__ __device__ inline int spw_off_tau(const SCfg &c) { return align16(spw_off_slots(c) + c.kcap * 4); }
+__host__ __device__ inline int spw_off_hint(const SCfg &c) { return spw_off_tau(c) + 64; }
+__host__ __device__ inline int spw_off_octs(const SCfg &c) { return spw_off_hint(c) + 128; }
+__host__ __device__ inline int spw_off_sub(const SCfg &c) { return spw_off_octs(c) + c.kcap; }
+__host__ __device__ inline int spw_bytes(const SCfg &c) { return align16(spw_off_sub(c) + (c.cs >> 1) * 2); }
+// solve kernel
+//   CTA : [tri LUT u16 x ntri][block points per structure f64 x 3*nst*ndb]
+//   warp: [P f64 x ntri]                        pristine bordered system (persists)
+//         [px,py,pz,va,ve f64 x ndp]            neighbours by matrix position
+//         [ut f64 x 3*nst*(ndp+ndb)]            their coordinates in structure space, then
+//                                               the node's block points (columns ndp..)
+//         [pid,newpos,newid,cur i32 x ndp]      sample id by position / fill list / this node
+//         [pivot rows f64 x 2*urow][unode f64 x 3*nst]
+//         [part f64 x nsplit*napad]             block kriging: partial right-hand sides
+__host__ __device__ inline int b_off_udb(const BCfg &c) { return align16(c.ntri * 2); }
+__host__ __device__ inline int b_off_warp(const BCfg &c) { return align16(b_off_udb(c) + 3 * c.nst * c.ndb * 8); }
+__host__ __device__ inline int bpw_off_pos(const BCfg &c) { return align16(c.ntri * 8); }
+__host__ __device__ inline int bpw_off_ut(const BCfg &c) { return bpw_off_pos(c) + 5 * c.ndp * 8; }
+__host__ __device__ inline int bpw_off_ints(const BCfg &c) { return bpw_off_ut(c) + 3 * c.nst * (c.ndp + c.ndb) * 8; }
+__host__ __device__ inline int bpw_off_rows(const BCfg &c) { return align16(bpw_off_ints(c) + 4 * c.ndp * 4); }
+__host__ __device__ inline int bpw_off_unode(const BCfg &c) { return bpw_off_rows(c) + 2 * c.urow * 8; }
+__host__ __device__ inline int bpw_off_part(const BCfg &c) { return bpw_off_unode(c) + 3 * c.nst * 8; }
+__host__ __device__ inline int bpw_bytes(const BCfg &c)
 {
-    return align16(pw_off_hint(c) + 32 * 4 + c.kcap + (c.cs >> 1) * 2);
+    return align16(bpw_off_part(c) + (c.nsplit > 1 ? c.nsplit * c.napad * 8 : 0));
 }
 
 // ---------------------------------------------------------------------------
@@ -503,7 +522,7 @@ __device__ __forceinline__ int select_small(const K3dParams &P, double *keys, in
 // Scan `count` contiguous candidates (slots slot0..slot0+count) and append those within
 // the search radius -- and within the caller's exact per-octant upper bounds tau[] --
 // to the warp's list; prunes when the list could overflow.
-__device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &cfg,
+__device__ __forceinline__ int scan_candidates(const K3dParams &P, const int kcap,
                                                const NodeCtx &nc, int slot0, int count,
                                                const double *tau, double *keys, int *slots,
                                                unsigned char *octs, int K, int lane,
@@ -530,7 +549,7 @@ __device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &c
         unsigned m = __ballot_sync(FULL, in);
         if (m == 0u)
             continue;
-        if (K + 32 > cfg.kcap) { // rare: thin the list (sorted afterwards); re-derive octants
+        if (K + 32 > kcap) { // rare: thin the list (sorted afterwards); re-derive octants
             __syncwarp();
             K = prune_list_cold(P, nc, keys, slots, K, lane);
             for (int t = lane; t < K; t += 32) {
@@ -551,90 +570,92 @@ __device__ __forceinline__ int scan_candidates(const K3dParams &P, const KCfg &c
     return K;
 }
 // out-of-line copy for the global-memory fallback walk
-__device__ __noinline__ int scan_candidates_cold(const K3dParams &P, const KCfg &cfg,
+__device__ __noinline__ int scan_candidates_cold(const K3dParams &P, const int kcap,
                                                  const NodeCtx &nc, int slot0, int count,
                                                  const double *tau, double *keys, int *slots,
                                                  unsigned char *octs, int K, int lane)
 {
-    return scan_candidates(P, cfg, nc, slot0, count, tau, keys, slots, octs, K, lane);
+    return scan_candidates(P, kcap, nc, slot0, count, tau, keys, slots, octs, K, lane);
 }
 
 // ---------------------------------------------------------------------------
-// the fused kernel
+// tile geometry shared by both kernels
 // ---------------------------------------------------------------------------
-template <int AMAX>
-__global__ void __launch_bounds__(AMAX == 5 ? 256 : 512, AMAX == 5 ? K3D_SMALL_CTAS : 1)
-k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
-                 const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
-                 const __grid_constant__ KCfg cfg)
+struct Tile {
+    int sbx, sby, sbz;  // super block
+    int x0, y0, z0;     // first node (z clipped to the slab)
+    int tnx, tny, tnz;  // nodes per axis
+    int tnodes;
+    int zsb0;           // first node plane of the super block (unclipped)
+};
+
+__device__ __forceinline__ Tile tile_of_block(const K3dParams &P, const K3dInputs &in, int iz0,
+                                              int iz1)
+{
+    Tile T;
+    int tile = blockIdx.x;
+    T.sbx = tile % P.nxsup;
+    tile /= P.nxsup;
+    T.sby = tile % P.nysup;
+    T.sbz = tile / P.nysup;
+    T.x0 = in.nodex0[T.sbx];
+    T.y0 = in.nodey0[T.sby];
+    T.zsb0 = in.nodez0[T.sbz];
+    int z1 = in.nodez0[T.sbz + 1];
+    T.z0 = T.zsb0 > iz0 ? T.zsb0 : iz0;
+    z1 = z1 < iz1 ? z1 : iz1;
+    T.tnx = in.nodex0[T.sbx + 1] - T.x0;
+    T.tny = in.nodey0[T.sby + 1] - T.y0;
+    T.tnz = z1 - T.z0;
+    T.tnodes = (T.tnx > 0 && T.tny > 0 && T.tnz > 0) ? T.tnx * T.tny * T.tnz : 0;
+    return T;
+}
+
+// node t of the tile's boustrophedon path: consecutive t are grid neighbours
+__device__ __forceinline__ void snake_node(const Tile &T, int t, int &lx, int &ly, int &lz)
+{
+    lz = t / (T.tnx * T.tny);
+    const int rem = t - lz * (T.tnx * T.tny);
+    const int lyr = rem / T.tnx, lxr = rem - lyr * T.tnx;
+    ly = (lz & 1) ? T.tny - 1 - lyr : lyr;
+    lx = ((lz * T.tny + lyr) & 1) ? T.tnx - 1 - lxr : lxr;
+}
+
+// ---------------------------------------------------------------------------
+// SEARCH kernel: super-block neighbour search (super_block.py:163-317, repairs D3-D5)
+//   nbr[(node - slab)*ndmax + i]  neighbours of the node (sorted-sample indices); ordered
+//                                 by (distance, index) and -1 padded when `ordered`
+//   cnt[node - slab]              number of neighbours, min(nclose, ndmax)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4)
+k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const int iz0,
+                  const int iz1, int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
+                  int32_t *__restrict__ ncand_out, const int ordered,
+                  const __grid_constant__ SCfg cfg)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = cfg.warps * 32;
-    const int ndp = cfg.ndp;
 
-    uint16_t *tri = (uint16_t *)(smem + off_tri(cfg));
-    double *stx = (double *)(smem + off_stage(cfg));
+    double *stx = (double *)smem;
     double *sty = stx + cfg.cs;
     double *stz = sty + cfg.cs;
-    int *stidx = (int *)(smem + off_sidx(cfg));
-    int *chunk = (int *)(smem + off_chunk(cfg)); // [3][nthreads]: lo, cnt, off
-    double *udb = (double *)(smem + off_udb(cfg)); // [3*nst][ndb] block points, structure space
-    const int pwb = pw_bytes(cfg), o_warp0 = off_warp(cfg), o_pos = pw_off_pos(cfg),
-              o_ut = pw_off_ut(cfg), o_ints = pw_off_ints(cfg), o_keys = pw_off_keys(cfg);
-    unsigned char *wbase = smem + o_warp0 + warp * pwb;
-    double *Pm = (double *)wbase;
-    double *keys = (double *)(wbase + pw_off_keys(cfg));
-    int *slots = (int *)(wbase + pw_off_slots(cfg));
-    double *px = (double *)(wbase + pw_off_pos(cfg));
-    double *py = px + ndp, *pz = py + ndp, *va = pz + ndp, *ve = va + ndp;
-    double *ut = (double *)(wbase + pw_off_ut(cfg));
-    int *pslot = (int *)(wbase + pw_off_ints(cfg));
-    int *pid = pslot + ndp, *newpos = pid + ndp, *newslot = newpos + ndp;
-    const int ucols = ndp + cfg.ndb; // columns of ut: neighbours by position, then block points
-    double *rows = (double *)(wbase + pw_off_rows(cfg));
-    double *tau = (double *)(wbase + pw_off_tau(cfg));
-    double *unode = tau + 8;
-    int *hint = (int *)(wbase + pw_off_hint(cfg));
-    unsigned char *octs = (unsigned char *)(hint + 32);
-    unsigned short *sub = (unsigned short *)(octs + cfg.kcap);
+    int *stidx = (int *)(smem + s_off_sidx(cfg));
+    int *chunk = (int *)(smem + s_off_chunk(cfg)); // [3][nthreads]: lo, cnt, off
+    unsigned char *wbase = smem + s_off_warp(cfg) + warp * spw_bytes(cfg);
+    double *keys = (double *)wbase;
+    int *slots = (int *)(wbase + spw_off_slots(cfg));
+    double *tau = (double *)(wbase + spw_off_tau(cfg));
+    int *hint = (int *)(wbase + spw_off_hint(cfg));
+    unsigned char *octs = wbase + spw_off_octs(cfg);
+    unsigned short *sub = (unsigned short *)(wbase + spw_off_sub(cfg));
 
     __shared__ int s_total, s_warpsum[32];
-    __shared__ double s_exptab[32]; // 2^(j/32)
-    __shared__ int s_job[16][6];     // per warp: npairs, npad, na, full, R, magic
-    __shared__ double s_jloc[16][3]; // per warp: node location
 
-    // ---- tile geometry: the grid nodes that fall in super block (sbx, sby, sbz) -------
-    int tile = blockIdx.x;
-    const int sbx = tile % P.nxsup;
-    tile /= P.nxsup;
-    const int sby = tile % P.nysup;
-    const int sbz = tile / P.nysup;
-    const int x0 = in.nodex0[sbx], x1 = in.nodex0[sbx + 1];
-    const int y0 = in.nodey0[sby], y1 = in.nodey0[sby + 1];
-    int z0 = in.nodez0[sbz], z1 = in.nodez0[sbz + 1];
-    z0 = z0 > iz0 ? z0 : iz0;
-    z1 = z1 < iz1 ? z1 : iz1;
-    const int tnx = x1 - x0, tny = y1 - y0, tnz = z1 - z0;
-    const int tnodes = tnx * tny * tnz;
-    if (tnodes <= 0)
+    const Tile T = tile_of_block(P, in, iz0, iz1);
+    if (T.tnodes <= 0)
         return;
-    // structure-space origin of the tile: first node of the super block (slab independent)
-    const double cx0 = P.xmn + x0 * P.xsiz, cy0 = P.ymn + y0 * P.ysiz,
-                 cz0 = P.zmn + in.nodez0[sbz] * P.zsiz;
-
-    if (tid < 32) s_exptab[tid] = exp2((double)tid * 0.03125);
-    // ---- triangular index LUT: e -> (row<<8 | col), row >= col --------------
-    for (int e = tid; e < cfg.ntri; e += nthreads) {
-        int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while (pk(r + 1, 0) <= e) r++;
-        while (pk(r, 0) > e) r--;
-        tri[e] = (uint16_t)((r << 8) | (e - pk(r, 0)));
-    }
-    // ---- block discretisation offsets in every structure's coordinates -------
-    for (int j = tid; j < P.ndb; j += nthreads)
-        transform_point_cold(P, Q, in.dbxyz[j], in.dbxyz[P.ndb + j], in.dbxyz[2 * P.ndb + j],
-                             udb, P.ndb, j);
+    const int sbx = T.sbx, sby = T.sby, sbz = T.sbz;
 
     // ---- stage the candidate samples of this tile (ascending sorted index) ---
     bool staged = true;
@@ -642,7 +663,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         int total = 0;
         for (int r0 = 0; r0 < in.nruns; r0 += nthreads) {
             int r = r0 + tid;
-            int lo = 0, cnt = 0;
+            int lo = 0, n = 0;
             if (r < in.nruns) {
                 const int16_t *rn = in.runs + 4 * r;
                 int by = sby + rn[2], bz = sbz + rn[3];
@@ -653,11 +674,11 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     if (bx0 <= bx1) {
                         int b = (bz * P.nysup + by) * P.nxsup;
                         lo = in.sbstart[b + bx0];
-                        cnt = in.sbstart[b + bx1 + 1] - lo;
+                        n = in.sbstart[b + bx1 + 1] - lo;
                     }
                 }
             }
-            int incl = cnt; // CTA-wide exclusive scan of cnt
+            int incl = n; // CTA-wide exclusive scan of n
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 int v = __shfl_up_sync(FULL, incl, d);
@@ -672,8 +693,8 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 ctot += v;
             }
             chunk[tid] = lo;
-            chunk[nthreads + tid] = cnt;
-            chunk[2 * nthreads + tid] = total + woff + incl - cnt;
+            chunk[nthreads + tid] = n;
+            chunk[2 * nthreads + tid] = total + woff + incl - n;
             total += ctot;
             __syncthreads();
             if (total <= cfg.cs) {
@@ -696,24 +717,8 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         staged = s_total <= cfg.cs;
     }
     const int ncand = s_total;
-    const double *db = in.dbxyz;
     const size_t slab_off = (size_t)iz0 * P.nx * P.ny;
     const unsigned ltm = (1u << lane) - 1u;
-    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
-    const int mdt = P.mdt;
-    // block kriging: a sample's ndb block-point covariances are split into nsplit work
-    // items of <= 4 points so that the pooled rounds stay evenly sized
-    // (partial sums go to the then idle search-list area and are added up in a fixed
-    // order by the owning warp, so results do not depend on warp scheduling)
-    const int napad_max = (P.ndmax + 31) & ~31;
-    int nsplit = 1;
-    if (P.ndb > 1) {
-        nsplit = (P.ndb + 3) >> 2;
-        const int cap = ((cfg.kcap * 3) >> 1) / napad_max;
-        nsplit = nsplit < cap ? nsplit : cap;
-        nsplit = nsplit < 1 ? 1 : nsplit;
-    }
-    const bool has_ext = (P.ktype == 2 || P.ktype == 3);
 
     NodeCtx nc;
     nc.qx = staged ? stx : in.sx;
@@ -722,10 +727,9 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
 
     // ---- each warp walks a contiguous piece of a boustrophedon path through the tile:
     //      consecutive nodes are grid neighbours, so their neighbourhoods overlap ---------
-    const int per = (tnodes + cfg.warps - 1) / cfg.warps;
-    const int t_begin = warp * per, t_end = (t_begin + per < tnodes) ? t_begin + per : tnodes;
-    int nprev = -1; // neighbours of the previous node whose covariances are still in Pm
-    int nhint = -1; // previous node's nearest candidates listed in hint[]
+    const int per = (T.tnodes + cfg.warps - 1) / cfg.warps;
+    const int t_begin = warp * per, t_end = (t_begin + per < T.tnodes) ? t_begin + per : T.tnodes;
+    int nhint = -1; // previous node's neighbours listed in hint[]
 
     // ---- candidates that can matter to this walk ------------------------------------------
     // A sample farther from the centre of the walk's bounding box than radius + rho (rho =
@@ -735,10 +739,8 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     if (staged && t_begin < t_end) {
         int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
         for (int t = t_begin + lane; t < t_end; t += 32) {
-            const int lz = t / (tnx * tny), rem = t - lz * (tnx * tny);
-            const int lyr = rem / tnx, lxr = rem - lyr * tnx;
-            const int ly = (lz & 1) ? tny - 1 - lyr : lyr;
-            const int lx = ((lz * tny + lyr) & 1) ? tnx - 1 - lxr : lxr;
+            int lx, ly, lz;
+            snake_node(T, t, lx, ly, lz);
             lo[0] = min(lo[0], lx); hi[0] = max(hi[0], lx);
             lo[1] = min(lo[1], ly); hi[1] = max(hi[1], ly);
             lo[2] = min(lo[2], lz); hi[2] = max(hi[2], lz);
@@ -748,9 +750,9 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             lo[k] = __reduce_min_sync(FULL, lo[k]);
             hi[k] = __reduce_max_sync(FULL, hi[k]);
         }
-        const double bcx = P.xmn + (x0 + 0.5 * (lo[0] + hi[0])) * P.xsiz,
-                     bcy = P.ymn + (y0 + 0.5 * (lo[1] + hi[1])) * P.ysiz,
-                     bcz = P.zmn + (z0 + 0.5 * (lo[2] + hi[2])) * P.zsiz;
+        const double bcx = P.xmn + (T.x0 + 0.5 * (lo[0] + hi[0])) * P.xsiz,
+                     bcy = P.ymn + (T.y0 + 0.5 * (lo[1] + hi[1])) * P.ysiz,
+                     bcz = P.zmn + (T.z0 + 0.5 * (lo[2] + hi[2])) * P.zsiz;
         const double ex = 0.5 * (hi[0] - lo[0]) * fabs(P.xsiz), ey = 0.5 * (hi[1] - lo[1]) * fabs(P.ysiz),
                      ez = 0.5 * (hi[2] - lo[2]) * fabs(P.zsiz);
         const double *rs = P.rotmat + 9 * P.nst;
@@ -776,23 +778,211 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         __syncwarp();
     }
 
-    for (int tt = 0; tt < per; tt++) {
-        const int t = t_begin + tt;
-        const bool active = t < t_end;
-        const int lz = t / (tnx * tny), rem = t - lz * (tnx * tny);
-        const int lyr = rem / tnx, lxr = rem - lyr * tnx;
-        const int ly = (lz & 1) ? tny - 1 - lyr : lyr;
-        const int lx = ((lz * tny + lyr) & 1) ? tnx - 1 - lxr : lxr;
-        const int ix = x0 + lx, iy = y0 + ly, iz = z0 + lz;
-        const size_t node = ((size_t)iz * P.ny + iy) * P.nx + ix;
-        const size_t o = node - slab_off;
+    for (int t = t_begin; t < t_end; t++) {
+        int lx, ly, lz;
+        snake_node(T, t, lx, ly, lz);
+        const int ix = T.x0 + lx, iy = T.y0 + ly, iz = T.z0 + lz;
+        const size_t o = (((size_t)iz * P.ny + iy) * P.nx + ix) - slab_off;
         // krige3d.py:307-309: xmn + ix*xsiz, multiply then add, unfused
         nc.xloc = __dadd_rn(P.xmn, __dmul_rn((double)ix, P.xsiz));
         nc.yloc = __dadd_rn(P.ymn, __dmul_rn((double)iy, P.ysiz));
         nc.zloc = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
+        int tested = 0;
+
+        // ---- 0. exact upper bounds from the previous node's neighbours ----------------
+        // Any set of samples bounds the selection: once `need` of them (noct per octant, or
+        // ndmax overall) are seen within the radius in an octant, nothing farther than the
+        // farthest of those can be selected there.
+        {
+            double mytau = P.radsqd;
+            if (nhint > 0) {
+                const double *rs = P.rotmat + 9 * P.nst;
+                const int noctants = P.noct > 0 ? 8 : 1;
+                const int need = P.noct > 0 ? P.noct : P.ndmax;
+                int cq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                unsigned bh = 0, bl = 0; // lane q: running max of octant q's first `need`
+                for (int h0 = 0; h0 < nhint; h0 += 32) {
+                    bool inr = false;
+                    int oq = 0;
+                    unsigned hi = 0, lo = 0;
+                    if (h0 + lane < nhint) {
+                        const int s = hint[h0 + lane];
+                        double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
+                               dz = __dsub_rn(nc.zloc, nc.qz[s]);
+                        double h = sqdist_exact(dx, dy, dz, rs);
+                        inr = !(h > P.radsqd);
+                        oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
+                        hi = (unsigned)__double2hiint(h);
+                        lo = (unsigned)__double2loint(h);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (q < noctants) {
+                            const unsigned mq = __ballot_sync(FULL, inr && oq == q);
+                            const bool mine = inr && oq == q && cq[q] + __popc(mq & ltm) < need;
+                            cq[q] += __popc(mq);
+                            const unsigned mh = __reduce_max_sync(FULL, mine ? hi : 0u);
+                            const unsigned ml = __reduce_max_sync(FULL, (mine && hi == mh) ? lo : 0u);
+                            if (lane == q && (mh > bh || (mh == bh && ml > bl))) { bh = mh; bl = ml; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (lane == q && cq[q] >= need) mytau = __hiloint2double((int)bh, (int)bl);
+            }
+            if (lane < 8) tau[lane] = mytau;
+            __syncwarp();
+        }
+
+        // ---- 1. scan ---------------------------------------------------------------------
+        int K = 0;
+        if (staged) {
+            NodeCtx ns = nc; // staged coordinates: plain shared-memory pointers
+            ns.qx = stx; ns.qy = sty; ns.qz = stz;
+            if (nsubw >= 0) {
+                tested = nsubw;
+                K = scan_candidates(P, cfg.kcap, ns, 0, nsubw, tau, keys, slots, octs, K, lane, sub);
+            } else {
+                tested = ncand;
+                K = scan_candidates(P, cfg.kcap, ns, 0, ncand, tau, keys, slots, octs, K, lane);
+            }
+        } else { // tile too dense for the stage: walk the runs in global memory
+            for (int r = 0; r < in.nruns; r++) {
+                const int16_t *rn = in.runs + 4 * r;
+                int by = sby + rn[2], bz = sbz + rn[3];
+                if (by < 0 || by >= P.nysup || bz < 0 || bz >= P.nzsup) continue;
+                int bx0 = sbx + rn[0], bx1 = sbx + rn[1];
+                bx0 = bx0 < 0 ? 0 : bx0;
+                bx1 = bx1 >= P.nxsup ? P.nxsup - 1 : bx1;
+                if (bx0 > bx1) continue;
+                int b = (bz * P.nysup + by) * P.nxsup;
+                int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
+                K = scan_candidates_cold(P, cfg.kcap, nc, lo, hi - lo, tau, keys, slots, octs, K, lane);
+                tested += hi - lo;
+            }
+        }
+        __syncwarp();
+        // ---- 2. select: which candidates the reference keeps (super_block.py:313-316 + octants)
+        if (K <= 64) {
+            K = select_small(P, keys, slots, octs, K, lane);
+            if (ordered && K > 1) { // reported lists are ordered by (distance, index)
+                const int n = K <= 32 ? 32 : 64;
+                for (int e = K + lane; e < n; e += 32) {
+                    keys[e] = __longlong_as_double(0x7ff0000000000000LL);
+                    slots[e] = 0x7fffffff;
+                }
+                __syncwarp();
+                warp_bitonic(keys, slots, n, lane);
+            }
+        } else if (staged) {
+            NodeCtx ns = nc;
+            ns.qx = stx; ns.qy = sty; ns.qz = stz;
+            K = prune_list(P, ns, keys, slots, K, lane);
+        } else {
+            K = prune_list_cold(P, nc, keys, slots, K, lane);
+        }
+        nhint = K < K3D_NHINT ? K : K3D_NHINT; // this node's neighbours seed the next bounds
+        if (lane < nhint) hint[lane] = slots[lane];
+        const int na = K < P.ndmax ? K : P.ndmax; // krige3d.py:356-375
+        __syncwarp();
+        for (int i = lane; i < (ordered ? P.ndmax : na); i += 32)
+            nbr[o * P.ndmax + i] = i < na ? (staged ? stidx[slots[i]] : slots[i]) : -1;
+        if (lane == 0) {
+            cnt[o] = na;
+            if (ncand_out) ncand_out[o] = tested;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SOLVE kernel: kriging system assembly (krige3d.py:470-583, 748-801, 838-875), solve and
+// estimate (krige3d.py:590-614) from the neighbour lists of the search kernel
+// ---------------------------------------------------------------------------
+template <int AMAX>
+__global__ void __launch_bounds__(AMAX == 5 ? 256 : 640, AMAX == 5 ? K3D_SMALL_CTAS : 1)
+k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
+                 const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
+                 const int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
+                 const __grid_constant__ BCfg cfg)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = cfg.warps * 32;
+    const int ndp = cfg.ndp;
+
+    uint16_t *tri = (uint16_t *)smem;
+    double *udb = (double *)(smem + b_off_udb(cfg)); // [3*nst][ndb] block points, structure space
+    const int pwb = bpw_bytes(cfg), o_warp0 = b_off_warp(cfg), o_pos = bpw_off_pos(cfg),
+              o_ut = bpw_off_ut(cfg), o_ints = bpw_off_ints(cfg), o_part = bpw_off_part(cfg);
+    unsigned char *wbase = smem + o_warp0 + warp * pwb;
+    double *Pm = (double *)wbase;
+    double *px = (double *)(wbase + o_pos);
+    double *py = px + ndp, *pz = py + ndp, *va = pz + ndp, *ve = va + ndp;
+    double *ut = (double *)(wbase + o_ut);
+    int *pid = (int *)(wbase + o_ints);
+    int *newpos = pid + ndp, *newid = newpos + ndp, *cur = newid + ndp;
+    const int ucols = ndp + cfg.ndb; // columns of ut: neighbours by position, then block points
+    double *rows = (double *)(wbase + bpw_off_rows(cfg));
+    double *unode = (double *)(wbase + bpw_off_unode(cfg));
+    double *part = (double *)(wbase + o_part);
+
+    __shared__ double s_exptab[32];  // 2^(j/32)
+    __shared__ int s_job[20][6];     // per warp: npairs, npad, na, full, R, magic
+    __shared__ double s_jloc[20][3]; // per warp: node location
+
+    const Tile T = tile_of_block(P, in, iz0, iz1);
+    if (T.tnodes <= 0)
+        return;
+    // structure-space origin of the tile: first node of the super block (slab independent)
+    const double cx0 = P.xmn + T.x0 * P.xsiz, cy0 = P.ymn + T.y0 * P.ysiz,
+                 cz0 = P.zmn + T.zsb0 * P.zsiz;
+
+    if (tid < 32) s_exptab[tid] = exp2((double)tid * 0.03125);
+    // ---- triangular index LUT: e -> (row<<8 | col), row >= col --------------
+    for (int e = tid; e < cfg.ntri; e += nthreads) {
+        int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while (pk(r + 1, 0) <= e) r++;
+        while (pk(r, 0) > e) r--;
+        tri[e] = (uint16_t)((r << 8) | (e - pk(r, 0)));
+    }
+    // ---- block discretisation offsets in every structure's coordinates -------
+    for (int j = tid; j < P.ndb; j += nthreads)
+        transform_point_cold(P, Q, in.dbxyz[j], in.dbxyz[P.ndb + j], in.dbxyz[2 * P.ndb + j],
+                             udb, P.ndb, j);
+    __syncthreads();
+
+    const double *db = in.dbxyz;
+    const size_t slab_off = (size_t)iz0 * P.nx * P.ny;
+    const unsigned ltm = (1u << lane) - 1u;
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    const int mdt = P.mdt;
+    // block kriging: a sample's ndb block-point covariances are split into nsplit work items
+    // of a few points so that the pooled rounds stay evenly sized; the partial sums are added
+    // up in a fixed order by the owning warp (results do not depend on warp scheduling)
+    const int nsplit = cfg.nsplit, napad_max = cfg.napad;
+    const bool has_ext = (P.ktype == 2 || P.ktype == 3);
+
+    // ---- each warp walks a contiguous piece of the tile's boustrophedon path ------------
+    const int per = (T.tnodes + cfg.warps - 1) / cfg.warps;
+    const int t_begin = warp * per, t_end = (t_begin + per < T.tnodes) ? t_begin + per : T.tnodes;
+    int nprev = -1; // neighbours of the previous node whose covariances are still in Pm
+
+    for (int tt = 0; tt < per; tt++) {
+        const int t = t_begin + tt;
+        const bool active = t < t_end;
+        int lx = 0, ly = 0, lz = 0;
+        if (active) snake_node(T, t, lx, ly, lz);
+        const int ix = T.x0 + lx, iy = T.y0 + ly, iz = T.z0 + lz;
+        const size_t o = (((size_t)iz * P.ny + iy) * P.nx + ix) - slab_off;
+        // krige3d.py:307-309: xmn + ix*xsiz, multiply then add, unfused
+        const double xloc = __dadd_rn(P.xmn, __dmul_rn((double)ix, P.xsiz));
+        const double yloc = __dadd_rn(P.ymn, __dmul_rn((double)iy, P.ysiz));
+        const double zloc = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
         double est = NaN, var = NaN;
         int status = K3D_ST_OK;
-        int na = 0, tested = 0;
+        int na = 0;
         double extest = 0.0, resce = 0.0, skmean = P.skmean;
 
         bool live = active;
@@ -805,139 +995,42 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             resce = P.maxcov / fmax(extest, 0.0001);
             if (P.ktype == 2) skmean = extest;
         }
-
         if (live) {
-            // ---- 0. exact upper bounds from the previous node's candidates ----------------
-            // Any set of samples bounds the selection: once `need` of them (noct per octant,
-            // or ndmax overall) are seen within the radius in an octant, nothing farther than
-            // the farthest of those can be selected there.  The previous node's nearest
-            // candidates, taken in their old distance order, give almost tight bounds.
-            {
-                double mytau = P.radsqd;
-                if (nhint > 0) {
-                    const double *rs = P.rotmat + 9 * P.nst;
-                    const int noctants = P.noct > 0 ? 8 : 1;
-                    const int need = P.noct > 0 ? P.noct : P.ndmax;
-                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    unsigned bh = 0, bl = 0; // lane q: running max of octant q's first `need`
-                    for (int h0 = 0; h0 < nhint; h0 += 32) {
-                        bool inr = false;
-                        int oq = 0;
-                        unsigned hi = 0, lo = 0;
-                        if (h0 + lane < nhint) {
-                            const int s = hint[h0 + lane];
-                            double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
-                                   dz = __dsub_rn(nc.zloc, nc.qz[s]);
-                            double h = sqdist_exact(dx, dy, dz, rs);
-                            inr = !(h > P.radsqd);
-                            oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
-                            hi = (unsigned)__double2hiint(h);
-                            lo = (unsigned)__double2loint(h);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            if (q < noctants) {
-                                const unsigned mq = __ballot_sync(FULL, inr && oq == q);
-                                const bool mine = inr && oq == q && cnt[q] + __popc(mq & ltm) < need;
-                                cnt[q] += __popc(mq);
-                                const unsigned mh = __reduce_max_sync(FULL, mine ? hi : 0u);
-                                const unsigned ml = __reduce_max_sync(FULL, (mine && hi == mh) ? lo : 0u);
-                                if (lane == q && (mh > bh || (mh == bh && ml > bl))) { bh = mh; bl = ml; }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-                        if (lane == q && cnt[q] >= need) mytau = __hiloint2double((int)bh, (int)bl);
-                }
-                if (lane < 8) tau[lane] = mytau;
-                __syncwarp();
-            }
-
-            // ---- 1. neighbour search ------------------------------------------
-            int K = 0;
-            if (staged) {
-                NodeCtx ns = nc; // staged coordinates: plain shared-memory pointers
-                ns.qx = stx; ns.qy = sty; ns.qz = stz;
-                if (nsubw >= 0) {
-                    tested = nsubw;
-                    K = scan_candidates(P, cfg, ns, 0, nsubw, tau, keys, slots, octs, K, lane, sub);
-                } else {
-                    tested = ncand;
-                    K = scan_candidates(P, cfg, ns, 0, ncand, tau, keys, slots, octs, K, lane);
-                }
-            } else { // tile too dense for the stage: walk the runs in global memory
-                for (int r = 0; r < in.nruns; r++) {
-                    const int16_t *rn = in.runs + 4 * r;
-                    int by = sby + rn[2], bz = sbz + rn[3];
-                    if (by < 0 || by >= P.nysup || bz < 0 || bz >= P.nzsup) continue;
-                    int bx0 = sbx + rn[0], bx1 = sbx + rn[1];
-                    bx0 = bx0 < 0 ? 0 : bx0;
-                    bx1 = bx1 >= P.nxsup ? P.nxsup - 1 : bx1;
-                    if (bx0 > bx1) continue;
-                    int b = (bz * P.nysup + by) * P.nxsup;
-                    int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
-                    K = scan_candidates_cold(P, cfg, nc, lo, hi - lo, tau, keys, slots, octs, K, lane);
-                    tested += hi - lo;
-                }
-            }
+            na = cnt[o];
+            for (int i = lane; i < na; i += 32) cur[i] = nbr[o * P.ndmax + i];
             __syncwarp();
-            // select: which candidates the reference keeps (super_block.py:313-316 + octants)
-            if (K <= 64) {
-                K = select_small(P, keys, slots, octs, K, lane);
-                if (out.nbr_idx && K > 1) { // reported lists are ordered by (distance, index)
-                    const int n = K <= 32 ? 32 : 64;
-                    for (int t = K + lane; t < n; t += 32) {
-                        keys[t] = __longlong_as_double(0x7ff0000000000000LL);
-                        slots[t] = 0x7fffffff;
-                    }
-                    __syncwarp();
-                    warp_bitonic(keys, slots, n, lane);
-                }
-            } else if (staged) {
-                NodeCtx ns = nc;
-                ns.qx = stx; ns.qy = sty; ns.qz = stz;
-                K = prune_list(P, ns, keys, slots, K, lane);
-            } else {
-                K = prune_list_cold(P, nc, keys, slots, K, lane);
-            }
-            nhint = K < K3D_NHINT ? K : K3D_NHINT; // this node's neighbours seed the next bounds
-            if (lane < nhint) hint[lane] = slots[lane];
-            na = K < P.ndmax ? K : P.ndmax; // krige3d.py:356-375
-            __syncwarp();
-            if (out.nbr_idx) {
-                for (int i = lane; i < P.ndmax; i += 32)
-                    out.nbr_idx[o * P.ndmax + i] = i < na ? (staged ? stidx[slots[i]] : slots[i]) : -1;
-            }
         }
 
         bool solve = false;
         if (!live) {
-            nprev = nhint = -1;
-            if (out.nbr_idx && active)
-                for (int i = lane; i < P.ndmax; i += 32) out.nbr_idx[o * P.ndmax + i] = -1;
+            nprev = -1;
+            if (active) { // the reference returns before searching: report no neighbours
+                if (lane == 0) cnt[o] = 0;
+                if (out.nbr_idx)
+                    for (int i = lane; i < P.ndmax; i += 32) out.nbr_idx[o * P.ndmax + i] = -1;
+            }
         } else if (na < P.ndmin || na == 0) { // krige3d.py:377, repair D15
             status = K3D_ST_NOT_ENOUGH_DATA;
-            nprev = nhint = -1;
+            nprev = -1;
         } else if (na <= mdt) { // krige3d.py:383
             status = K3D_ST_NOT_ENOUGH_DRIFT;
-            nprev = nhint = -1;
+            nprev = -1;
         } else {
             solve = true;
         }
         const int N = na + mdt, R = N + 1;
         if (solve) {
-            // ---- 2. map the neighbours to matrix positions ---------------------------
+            // ---- 1. map the neighbours to matrix positions ---------------------------
             // A neighbour kept from the previous node keeps its row/column, so the
             // sample-sample covariances already in Pm stay valid; newcomers take the
-            // positions that were freed.  (newpos[], newslot[]) lists what must be filled.
+            // positions that were freed.  (newpos[], newid[]) lists what must be filled.
             int nnew = na;
             bool full = true;
             if (cfg.reuse && nprev == na && na <= 32) {
                 int pos = -1;
-                const int myslot = lane < na ? slots[lane] : -1;
+                const int myid = lane < na ? cur[lane] : -1;
                 for (int p = 0; p < na; p++)
-                    if (pslot[p] == myslot) pos = p;
+                    if (pid[p] == myid) pos = p;
                 if (lane >= na) pos = -2;
                 const unsigned used = __reduce_or_sync(FULL, pos >= 0 ? (1u << pos) : 0u);
                 const unsigned unm = __ballot_sync(FULL, pos == -1);
@@ -950,23 +1043,21 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         const int r = __popc(unm & ltm);
                         for (int k = 0; k < r; k++) freem &= freem - 1u;
                         newpos[r] = __ffs(freem) - 1;
-                        newslot[r] = myslot;
+                        newid[r] = myid;
                     }
                 }
             }
-            if (full) { // positions = distance order
+            if (full) { // positions = list order
                 for (int i = lane; i < na; i += 32) {
                     newpos[i] = i;
-                    newslot[i] = slots[i];
+                    newid[i] = cur[i];
                 }
             }
             __syncwarp();
             for (int k = lane; k < nnew; k += 32) {
-                const int pos = newpos[k], sl = newslot[k];
-                const int g = staged ? stidx[sl] : sl;
-                pslot[pos] = sl;
+                const int pos = newpos[k], g = newid[k];
                 pid[pos] = g;
-                const double x = nc.qx[sl], y = nc.qy[sl], z = nc.qz[sl];
+                const double x = in.sx[g], y = in.sy[g], z = in.sz[g];
                 px[pos] = x; py[pos] = y; pz[pos] = z;
                 const double v = in.sv[g], e = has_ext ? in.ssec[g] : 0.0;
                 va[pos] = (P.ktype == 0) ? v - P.skmean : (P.ktype == 2 ? v - e : v);
@@ -975,7 +1066,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             }
             // the node and its block points in every structure's coordinates (columns ndp..)
             if (lane == 0)
-                transform_point_cold(P, Q, nc.xloc - cx0, nc.yloc - cy0, nc.zloc - cz0, unode, 1, 0);
+                transform_point_cold(P, Q, xloc - cx0, yloc - cy0, zloc - cz0, unode, 1, 0);
             __syncwarp();
             for (int k = lane; k < 3 * P.nst * P.ndb; k += 32) {
                 const int row = k / P.ndb, j = k - row * P.ndb;
@@ -992,7 +1083,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 s_job[warp][3] = full ? 1 : 0;
                 s_job[warp][4] = R;
                 s_job[warp][5] = (65536 + na - 1) / na;
-                s_jloc[warp][0] = nc.xloc; s_jloc[warp][1] = nc.yloc; s_jloc[warp][2] = nc.zloc;
+                s_jloc[warp][0] = xloc; s_jloc[warp][1] = yloc; s_jloc[warp][2] = zloc;
             }
         }
         if (!solve && lane == 0) {
@@ -1001,12 +1092,12 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         }
         K3D_PHASE_BARRIER();
 
-        // ---- 3. covariances of every node in flight, pooled over the CTA ---------------
+        // ---- 2. covariances of every node in flight, pooled over the CTA ---------------
         // One work loop evaluates every covariance the nodes need (krige3d.py:748-801); the
         // items of all warps are dealt out evenly, 32 at a time, so that no warp waits for
         // another's longer list.  Per warp (job):
         //   items [0, npairs)           sample-sample pairs: all, or those with a newcomer
-        //   items [npad, npad + na)     sample i against the node's ndb block points
+        //   items [npad, npad + ...)    sample i against (a part of) the node's block points
         {
             int next = 0; // warp that takes the next round of 32 items
             for (int jw = 0; jw < cfg.warps; jw++) {
@@ -1025,18 +1116,18 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     const double *jpx = (const double *)(jb + o_pos);
                     const double *jpy = jpx + ndp, *jpz = jpy + ndp;
                     const double *jut = (const double *)(jb + o_ut);
-                    const int *jnewpos = (const int *)(jb + o_ints) + 2 * ndp;
-                    double *jscratch = (double *)(jb + o_keys);
+                    const int *jnewpos = (const int *)(jb + o_ints) + ndp;
+                    double *jpart = (double *)(jb + o_part);
                     for (int w = (r0 << 5) + lane; w < jlen; w += cfg.warps << 5) {
                         int p1 = 0, p2 = 0, nsub = 0, sub0 = 0;
                         const bool rhs = w >= jnpad;
-                        int part = 0;
+                        int prt = 0;
                         if (rhs) { // sample p1 against block points [sub0, sub0 + nsub)
                             p1 = w - jnpad;
                             if (nsplit > 1) {
-                                while (p1 >= jnapad) { p1 -= jnapad; part++; } // uniform per round
-                                sub0 = (part * P.ndb) / nsplit;
-                                nsub = ((part + 1) * P.ndb) / nsplit - sub0;
+                                while (p1 >= jnapad) { p1 -= jnapad; prt++; } // uniform per round
+                                sub0 = (prt * P.ndb) / nsplit;
+                                nsub = ((prt + 1) * P.ndb) / nsplit - sub0;
                             } else {
                                 nsub = P.ndb;
                             }
@@ -1080,7 +1171,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         if (rhs) {
                             if (nsub) { // b row (krige3d.py:797-798)
                                 if (nsplit > 1)
-                                    jscratch[part * napad_max + p1] = acc;
+                                    jpart[prt * napad_max + p1] = acc;
                                 else
                                     jPm[pk(jR - p1, 1)] = acc;
                             }
@@ -1097,7 +1188,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 double cb = Pm[pk(R, 1)];
                 if (nsplit > 1) {
                     cb = 0.0;
-                    for (int part = 0; part < nsplit; part++) cb += keys[part * napad_max];
+                    for (int q = 0; q < nsplit; q++) cb += part[q * napad_max];
                     cb /= (double)P.ndb;
                 }
                 const double sw = cb / P.cbb;
@@ -1109,13 +1200,13 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 // data vector and constraint rows (krige3d.py:764-767, 493-583 with repair
                 // D6): they depend on the node and are rebuilt every time
                 for (int i = lane; i < na; i += 32) {
-                    const double x = px[i] - nc.xloc, y = py[i] - nc.yloc, z = pz[i] - nc.zloc;
+                    const double x = px[i] - xloc, y = py[i] - yloc, z = pz[i] - zloc;
                     const int ri = R - i;
                     Pm[pk(ri, ri)] = P.maxcov; // cova3(p, p)
                     Pm[pk(ri, 0)] = va[i];     // v row
                     if (nsplit > 1) { // b row from the partial sums (krige3d.py:797-798)
                         double cb = 0.0;
-                        for (int part = 0; part < nsplit; part++) cb += keys[part * napad_max + i];
+                        for (int q = 0; q < nsplit; q++) cb += part[q * napad_max + i];
                         Pm[pk(ri, 1)] = cb / (double)P.ndb;
                     }
                     if (P.itrend) Pm[pk(ri, 1)] = 0.0; // repair D10: kriging the trend
@@ -1157,7 +1248,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 }
                 __syncwarp();
 
-                // ---- 4. LDL^T elimination of the N pivots ---------------------------
+                // ---- 3. LDL^T elimination of the N pivots ---------------------------
                 if constexpr (AMAX > 0) {
                     RegSolve<AMAX>::run(Pm, R, rows, cfg.urow, lane, est, var);
                     nprev = na;
@@ -1178,9 +1269,7 @@ k3d_krige_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         if (lane == 0 && active) {
             out.est[o] = est;
             out.var[o] = var;
-            if (out.nbr_cnt) out.nbr_cnt[o] = na;
             if (out.status) out.status[o] = (uint8_t)status;
-            if (out.ncand) out.ncand[o] = tested;
         }
         __syncwarp();
     }
@@ -1262,77 +1351,130 @@ void make_prep(const K3dParams *p, KPrep *q)
     q->eps0s = K3D_EPS / (a0 * a0);
 }
 
-// Shared-memory plan: warps per CTA and stage capacity such that two CTAs share an SM
-// when possible.  `mean_cand` is the expected number of candidate samples per tile.
-int make_cfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_max, KCfg *c)
+// ---- search kernel plan: stage capacity and CTAs per SM --------------------------------
+// `mean_cand` is the expected number of candidate samples per tile, `tile_nodes` the mean
+// number of grid nodes per tile.
+int make_scfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_max, SCfg *c)
 {
-    // the small-system kernel is compiled for CTAs of at most 8 warps
-    const int max_warps = amax_for(p->ndmax + p->mdt + 2) == 5 ? 8 : 16;
     memset(c, 0, sizeof(*c));
-    c->rtot = p->ndmax + p->mdt + 2;
-    c->ntri = c->rtot * (c->rtot + 1) / 2;
-    c->ndp = (p->ndmax + 3) & ~3;
     c->keepmax = p->noct > 0 ? 8 * p->noct : p->ndmax;
     c->kcap = 128; // power of two: the bitonic network pads the list up to it
     while (c->kcap < c->keepmax + 64) c->kcap <<= 1;
-    c->nst = p->nst;
-    c->ndb = p->ndb;
-    const int amax = amax_for(c->rtot);
-    c->urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c->rtot;
-    c->reuse = amax > 0 ? 1 : 0;
+    // a warp's first node has no bounds from a predecessor: keep walks >= ~12 nodes
+    c->warps = tile_nodes >= 96.0 ? 8 : tile_nodes >= 48.0 ? 4 : 2;
     int want = roundup32((int)(2.0 * mean_cand) + 64);
     if (want < 256) want = 256;
     if (want > 4096) want = 4096;
     int floor_cs = roundup32((int)(1.4 * mean_cand) + 32);
     if (floor_cs < 128) floor_cs = 128;
     if (floor_cs > want) floor_cs = want;
-    // CTA shapes (CTAs per SM, warps per CTA).  The kernel is latency bound, so more warps
-    // per SM help, but every warp starts its walk with a full-cost node (no bounds, no
-    // covariance reuse), so short walks hurt: score = warps per SM * per / (per + 4) with
-    // per = nodes per warp and tile.  128 registers per thread cap an SM at 16 warps.
-    static const int shapes[][2] = {{2, 8}, {1, 16}, {1, 14}, {2, 6}, {1, 12}, {1, 10},
-                                    {2, 4}, {1, 8}, {1, 6}, {1, 4},
-                                    // small tiles (few nodes per super block): many small CTAs
-                                    {3, 5}, {4, 4}, {5, 3}, {8, 2}, {6, 2}, {4, 2}, {3, 4}};
-    double best = -1.0;
-    KCfg pick = *c;
-    for (unsigned i = 0; i < sizeof(shapes) / sizeof(shapes[0]); i++) {
-        const int ctas = shapes[i][0];
-        // the driver reserves 1 KB per CTA; 1.5 KB covers the kernel's static shared memory
-        const int budget = (smem_max + 1024) / ctas - 1024 - 1536;
-        c->warps = shapes[i][1];
-        if (c->warps > max_warps) continue;
-        c->cs = 0;
-        const int fixed = off_warp(*c) + c->warps * pw_bytes(*c);
-        // per candidate: 24 B coordinates + 4 B index in the stage, 1 B of short list per warp
-        int cs = ((budget - fixed - 64) / (28 + c->warps)) & ~31;
-        if (cs > want) cs = want;
-        if (cs < floor_cs) continue;
-        const double per = tile_nodes / c->warps;
-        const double score = ctas * c->warps * per / (per + 4.0);
-        if (score > best) {
-            best = score;
-            c->cs = cs;
-            c->pw_bytes = pw_bytes(*c);
-            c->smem_bytes = off_warp(*c) + c->warps * c->pw_bytes;
-            pick = *c;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int ctas = 6; ctas >= 1; ctas--) {
+            // the driver reserves 1 KB per CTA; 256 B covers the static shared memory
+            const int budget = (smem_max + 1024) / ctas - 1024 - 256;
+            c->cs = 0;
+            const int fixed = s_off_warp(*c) + c->warps * spw_bytes(*c);
+            // per candidate: 24 B coordinates + 4 B index in the stage, 1 B of short list per warp
+            int cs = ((budget - fixed - 64) / (28 + c->warps)) & ~31;
+            if (cs > want) cs = want;
+            if (cs >= (pass == 0 ? want : floor_cs)) {
+                c->cs = cs;
+                c->pw_bytes = spw_bytes(*c);
+                c->smem_bytes = s_off_warp(*c) + c->warps * c->pw_bytes;
+                return K3D_OK;
+            }
         }
-    }
-    if (best > 0.0) {
-        *c = pick;
-        return K3D_OK;
     }
     return K3D_ECAPACITY;
 }
 
-template <int AMAX>
-int launch_krige(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
-                 int iz0, int iz1, const KCfg &c, long long ntiles, cudaStream_t st)
+// ---- solve kernel plan: warps per CTA and CTAs per SM -------------------------------------
+int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
 {
-    CUDA_TRY(cudaFuncSetAttribute(k3d_krige_kernel<AMAX>,
+    memset(c, 0, sizeof(*c));
+    c->rtot = p->ndmax + p->mdt + 2;
+    c->ntri = c->rtot * (c->rtot + 1) / 2;
+    c->ndp = (p->ndmax + 3) & ~3;
+    c->nst = p->nst;
+    c->ndb = p->ndb;
+    const int amax = amax_for(c->rtot);
+    c->urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c->rtot;
+    c->reuse = amax > 0 ? 1 : 0;
+    c->napad = (p->ndmax + 31) & ~31;
+    c->nsplit = 1;
+    if (p->ndb > 1) { // right-hand side work items of <= 4 block points, at most 8 per sample
+        c->nsplit = (p->ndb + 3) >> 2;
+        if (c->nsplit > 8) c->nsplit = 8;
+    }
+    // The kernel is latency bound, so more warps per SM help, but every warp starts its walk
+    // with a full-cost node (no covariance reuse), so short walks hurt: score = warps per SM *
+    // per / (per + 4) with per = nodes per warp and tile.  Registers cap an SM at 20 warps
+    // (102 per thread; 24 warps of 85 for the small-system kernel, whose CTAs hold <= 8 warps).
+    const int max_cta_warps = amax == 5 ? 8 : 20, max_sm_warps = amax == 5 ? 24 : 20;
+    static const int shapes[][2] = {{2, 10}, {1, 20}, {1, 18}, {2, 8}, {1, 16}, {1, 14}, {2, 6},
+                                    {1, 12}, {1, 10}, {2, 4}, {1, 8}, {1, 6}, {1, 4},
+                                    {3, 8}, {3, 6}, {3, 5}, {4, 4}, {5, 3}, {8, 2}, {6, 2}, {4, 2},
+                                    {3, 4}, {12, 2}, {6, 4}};
+    double best = -1.0;
+    BCfg pick = *c;
+    int force_ctas = 0, force_warps = 0; // experiments: K3D_SOLVE_SHAPE="ctas,warps"
+    if (const char *e = getenv("K3D_SOLVE_SHAPE")) sscanf(e, "%d,%d", &force_ctas, &force_warps);
+    for (unsigned i = 0; i < sizeof(shapes) / sizeof(shapes[0]); i++) {
+        const int ctas = shapes[i][0], warps = shapes[i][1];
+        if (warps > max_cta_warps || ctas * warps > max_sm_warps) continue;
+        if (force_warps && (ctas != force_ctas || warps != force_warps)) continue;
+        // the driver reserves 1 KB per CTA; 1.5 KB covers the kernel's static shared memory
+        const int budget = (smem_max + 1024) / ctas - 1024 - 1536;
+        c->warps = warps;
+        const int bytes = b_off_warp(*c) + warps * bpw_bytes(*c);
+        if (bytes > budget) continue;
+        const double per = tile_nodes / warps;
+        const double score = ctas * warps * per / (per + 4.0);
+        if (score > best) {
+            best = score;
+            c->pw_bytes = bpw_bytes(*c);
+            c->smem_bytes = bytes;
+            pick = *c;
+        }
+    }
+    if (best <= 0.0) return K3D_ECAPACITY;
+    *c = pick;
+    return K3D_OK;
+}
+
+// Stream-ordered scratch for the neighbour lists comes from one memory pool per device
+// that keeps what it has been given (release threshold = max): the default pool hands
+// freed memory back to the OS at the next synchronisation, which costs more than the
+// search kernel itself when 2 GB are re-allocated on every call.
+int scratch_pool(int dev, cudaMemPool_t *pool)
+{
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    if (dev < 0 || dev >= 64) return fail(K3D_EINVAL, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        CUDA_TRY(cudaMemPoolCreate(&pools[dev], &props));
+        uint64_t keep = UINT64_MAX;
+        CUDA_TRY(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    *pool = pools[dev];
+    return K3D_OK;
+}
+
+template <int AMAX>
+int launch_solve(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
+                 int iz0, int iz1, const int32_t *nbr, int32_t *cnt, const BCfg &c,
+                 long long ntiles, cudaStream_t st)
+{
+    CUDA_TRY(cudaFuncSetAttribute(k3d_solve_kernel<AMAX>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
-    k3d_krige_kernel<AMAX><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(*p, *q, *in, *out,
-                                                                                iz0, iz1, c);
+    k3d_solve_kernel<AMAX><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(
+        *p, *q, *in, *out, iz0, iz1, nbr, cnt, c);
     CUDA_TRY(cudaGetLastError());
     return K3D_OK;
 }
@@ -1391,29 +1533,78 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
     CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const double nsb = (double)p->nxsup * p->nysup * p->nzsup;
     const double mean_cand = in->ntmpl > 0 ? (double)in->nd / nsb * in->ntmpl : 512.0;
-    KCfg c;
     const double tile_nodes = (double)p->nx * p->ny * p->nz / nsb;
-    if (make_cfg(p, mean_cand, tile_nodes, smem_max, &c) != K3D_OK)
+    SCfg sc;
+    BCfg bc;
+    if (make_scfg(p, mean_cand, tile_nodes, smem_max, &sc) != K3D_OK ||
+        make_bcfg(p, tile_nodes, smem_max, &bc) != K3D_OK)
         return fail(K3D_ECAPACITY, "ndmax/drift/discretisation exceed the shared memory of an SM");
-    // one CTA per super block; CTAs whose super block does not meet the slab exit at once
-    long long ntiles = (long long)p->nxsup * p->nysup * p->nzsup;
+    // one CTA per super block; CTAs whose super block does not meet the planes exit at once
+    const long long ntiles = (long long)p->nxsup * p->nysup * p->nzsup;
     if (ntiles > 0x7fffffffLL) return fail(K3D_EINVAL, "too many tiles");
     KPrep q;
     make_prep(p, &q);
-    switch (amax_for(c.rtot)) {
-    case 5: rc = launch_krige<5>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
-    case 9: rc = launch_krige<9>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
-    case 11: rc = launch_krige<11>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
-    default: rc = launch_krige<0>(p, &q, in, out, iz0, iz1, c, ntiles, st); break;
+    CUDA_TRY(cudaFuncSetAttribute(k3d_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  sc.smem_bytes));
+
+    // neighbour lists travel from the search kernel to the solve kernel through global
+    // memory: the caller's arrays when given, else stream-ordered scratch, at most ~2 GB at
+    // a time (the slab is then processed in runs of z-planes)
+    const size_t plane = (size_t)p->nx * p->ny;
+    const size_t per_plane = plane * ((out->nbr_idx ? 0 : (size_t)p->ndmax * 4) + (out->nbr_cnt ? 0 : 4));
+    int zstep = iz1 - iz0;
+    if (per_plane > 0) {
+        const size_t cap = (size_t)2 << 30;
+        size_t fit = cap / per_plane;
+        if (fit < 1) fit = 1;
+        if ((size_t)zstep > fit) zstep = (int)fit;
     }
+    int32_t *snbr = nullptr, *scnt = nullptr;
+    cudaMemPool_t pool = nullptr;
+    if (!out->nbr_idx || !out->nbr_cnt) {
+        rc = scratch_pool(dev, &pool);
+        if (rc) return rc;
+    }
+    if (!out->nbr_idx)
+        CUDA_TRY(cudaMallocFromPoolAsync((void **)&snbr, (size_t)zstep * plane * p->ndmax * 4, pool, st));
+    if (!out->nbr_cnt)
+        CUDA_TRY(cudaMallocFromPoolAsync((void **)&scnt, (size_t)zstep * plane * 4, pool, st));
+    for (int za = iz0; za < iz1 && rc == K3D_OK; za += zstep) {
+        const int zb = za + zstep < iz1 ? za + zstep : iz1;
+        const size_t shift = (size_t)(za - iz0) * plane; // nodes before this run in the slab
+        K3dInputs ci = *in;
+        if (ci.extgrid) ci.extgrid += shift;
+        K3dOutputs co = *out;
+        co.est += shift;
+        co.var += shift;
+        if (co.nbr_idx) co.nbr_idx += shift * p->ndmax;
+        if (co.nbr_cnt) co.nbr_cnt += shift;
+        if (co.status) co.status += shift;
+        if (co.ncand) co.ncand += shift;
+        int32_t *nbr = co.nbr_idx ? co.nbr_idx : snbr;
+        int32_t *cnt = co.nbr_cnt ? co.nbr_cnt : scnt;
+        k3d_search_kernel<<<(unsigned)ntiles, sc.warps * 32, sc.smem_bytes, st>>>(
+            *p, ci, za, zb, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc);
+        if (cudaGetLastError() != cudaSuccess) { rc = fail(K3D_ECUDA, "search kernel launch failed"); break; }
+        switch (amax_for(bc.rtot)) {
+        case 5: rc = launch_solve<5>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
+        case 9: rc = launch_solve<9>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
+        case 11: rc = launch_solve<11>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
+        default: rc = launch_solve<0>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
+        }
+        g_launch.launches += 2;
+    }
+    if (snbr) cudaFreeAsync(snbr, st);
+    if (scnt) cudaFreeAsync(scnt, st);
     if (rc) return rc;
     g_launch.grid = (int)ntiles;
-    g_launch.block = c.warps * 32;
-    g_launch.smem_bytes = c.smem_bytes;
-    g_launch.warps_per_cta = c.warps;
-    g_launch.stage_capacity = c.cs;
-    g_launch.list_capacity = c.kcap;
-    g_launch.launches += 1;
+    g_launch.block = bc.warps * 32;
+    g_launch.smem_bytes = bc.smem_bytes;
+    g_launch.warps_per_cta = bc.warps;
+    g_launch.stage_capacity = sc.cs;
+    g_launch.list_capacity = sc.kcap;
+    g_launch.search_block = sc.warps * 32;
+    g_launch.search_smem_bytes = sc.smem_bytes;
     return K3D_OK;
 }
 
