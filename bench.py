@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
 
-A "step" is one pass of the krige3d hot path (search + assembly + solve, one fused kernel)
+A "step" is one pass of the krige3d hot path (search kernel + assembly/solve kernel)
 over the whole synthetic grid of the chosen configuration (default c3 = BASELINE.json
 configs[2], the 256^3 / ndmax=32 ordinary-kriging case the metric is quoted on).  With N>1
 (torchrun, one rank per GPU) the grid is split into z-slabs, samples replicated, and each
@@ -274,7 +274,7 @@ def main():
                "breakdown_s": {k: round(v, 4) for k, v in ke.timings.items()},
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt[0]) * 1e3,
                "includes": "Krige3d(par, data).kt3d(): super-block set-up (binning, template "
-                           "kernel), pinned H2D of samples/index, fused kernel, D2H of "
+                           "kernel), pinned H2D of samples/index, search + solve kernels, D2H of "
                            "est/var/status" + ("; all-gather of slabs" if world > 1 else "")}
 
     if rank == 0:

@@ -1,24 +1,29 @@
 // k3d_kernels.cu -- sm_100a kernels and C ABI for the krige3d grid-estimation path.
 //
-// One fused kernel does, per grid node, what the reference's node loop does
+// Two kernels do, per grid node, what the reference's node loop does
 // (/root/reference/pygeostatistics/krige3d.py:302-403):
-//   1. super-block neighbour search        super_block.py:163-317 (repairs D3-D5)
-//   2. kriging system assembly             krige3d.py:470-583, 748-801, 838-875
-//   3. solve + estimate + variance         krige3d.py:590-614
+//   k3d_search_kernel   super-block neighbour search     super_block.py:163-317 (repairs D3-D5)
+//   k3d_solve_kernel    kriging system assembly          krige3d.py:470-583, 748-801, 838-875
+//                       solve + estimate + variance      krige3d.py:590-614
+// The neighbour lists travel between them through global memory (HBM is not the bound:
+// 128 B per node against 6.5 TB/s), which lets the light search run at 32 warps per SM
+// and the register-heavy solve at up to 20.
 //
 // Mapping to the machine (DESIGN.md has the full account):
 //   * one CTA per "tile" = the grid nodes that fall in one super block; all of them
 //     search the same super blocks, so the candidate samples are staged ONCE per CTA
 //     into shared memory as SoA tiles, in ascending sorted-sample order;
-//   * one warp per node: lanes scan the staged candidates with the reference's exact
-//     (FMA-free) anisotropic distance, compact the in-radius ones with ballots, sort
-//     them by (distance, index) with a shared-memory bitonic network, apply the octant
-//     rule with ballot prefix counts and keep the first ndmax;
+//   * one warp per node, each warp walking a boustrophedon path so that consecutive nodes
+//     are neighbours: lanes scan the candidates with the reference's exact (FMA-free)
+//     anisotropic distance under exact bounds inherited from the previous node, compact
+//     the hits with ballots and remove the surplus (octant rule, ndmax) by warp-wide
+//     lexicographic maxima;
 //   * the (n+mdt) system is assembled in shared memory in a mirrored packed-triangular
-//     layout, bordered by the right-hand side and the data vector, so that a single
-//     LDL^T elimination sweep (no pivoting: covariance block is SPD, the constraint
-//     Schur complement is definite) leaves the kriging variance and the estimate in
-//     the two border entries -- no triangular solves, no weights materialised.
+//     layout -- re-using the sample-sample covariances of the previous node -- bordered by
+//     the right-hand side and the data vector, so that a single register-resident LDL^T
+//     sweep (no pivoting: covariance block is SPD, the constraint Schur complement is
+//     definite) leaves the kriging variance and the estimate in the two border entries:
+//     no triangular solves, no weights materialised.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see build.py).
 #include <cuda_runtime.h>

@@ -8,7 +8,7 @@ Same constructor, parameter files, attributes and driver method as
     k.estimation, k.estimation_variance
 
 What differs is where the node loop (krige3d.py:302-411) runs: the super-block search,
-the kriging-system assembly and the solve are one fused sm_100a kernel reached through
+the kriging-system assembly and the solve are two sm_100a kernels reached through
 the C ABI of include/k3d.h.  There is no CPU fallback.
 
 Beyond the reference (it parses these but crashes on them):
