@@ -161,6 +161,9 @@ typedef struct K3dLaunchInfo {
     int32_t stage_capacity, list_capacity, launches;
     int32_t search_block, search_smem_bytes;        /* search kernel */
     int32_t _pad;
+    float search_ms, solve_ms; /* device time of the two kernels of the last run of planes
+                                  (CUDA events on the caller's stream; k3d_last_launch waits
+                                  for them) */
 } K3dLaunchInfo;
 int k3d_last_launch(K3dLaunchInfo *info);
 

@@ -55,7 +55,8 @@ class K3dLaunchInfo(C.Structure):
     _fields_ = [("grid", C.c_int32), ("block", C.c_int32), ("smem_bytes", C.c_int32),
                 ("warps_per_cta", C.c_int32), ("stage_capacity", C.c_int32),
                 ("list_capacity", C.c_int32), ("launches", C.c_int32),
-                ("search_block", C.c_int32), ("search_smem_bytes", C.c_int32), ("_pad", C.c_int32)]
+                ("search_block", C.c_int32), ("search_smem_bytes", C.c_int32), ("_pad", C.c_int32),
+                ("search_ms", C.c_float), ("solve_ms", C.c_float)]
 
 
 # every symbol include/k3d.h declares

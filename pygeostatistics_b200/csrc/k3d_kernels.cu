@@ -53,7 +53,10 @@
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local K3dLaunchInfo g_launch = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+thread_local K3dLaunchInfo g_launch = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.f, 0.f};
+thread_local cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+thread_local int g_ev_dev = -1;   // device the events belong to
+thread_local bool g_ev_pending = false;
 
 int fail(int code, const char *fmt, const char *detail = "")
 {
@@ -1497,6 +1500,13 @@ const char *k3d_last_error(void) { return g_err; }
 int k3d_last_launch(K3dLaunchInfo *info)
 {
     if (!info) return fail(K3D_EINVAL, "info is NULL");
+    if (g_ev_pending) {
+        g_ev_pending = false;
+        if (cudaEventSynchronize(g_ev[2]) == cudaSuccess) {
+            cudaEventElapsedTime(&g_launch.search_ms, g_ev[0], g_ev[1]);
+            cudaEventElapsedTime(&g_launch.solve_ms, g_ev[1], g_ev[2]);
+        }
+    }
     *info = g_launch;
     return K3D_OK;
 }
@@ -1564,6 +1574,10 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
         if (fit < 1) fit = 1;
         if ((size_t)zstep > fit) zstep = (int)fit;
     }
+    if (g_ev_dev != dev) { // per-thread timing events for k3d_last_launch
+        for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&g_ev[i]));
+        g_ev_dev = dev;
+    }
     int32_t *snbr = nullptr, *scnt = nullptr;
     cudaMemPool_t pool = nullptr;
     if (!out->nbr_idx || !out->nbr_cnt) {
@@ -1588,15 +1602,19 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
         if (co.ncand) co.ncand += shift;
         int32_t *nbr = co.nbr_idx ? co.nbr_idx : snbr;
         int32_t *cnt = co.nbr_cnt ? co.nbr_cnt : scnt;
+        cudaEventRecord(g_ev[0], st);
         k3d_search_kernel<<<(unsigned)ntiles, sc.warps * 32, sc.smem_bytes, st>>>(
             *p, ci, za, zb, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc);
         if (cudaGetLastError() != cudaSuccess) { rc = fail(K3D_ECUDA, "search kernel launch failed"); break; }
+        cudaEventRecord(g_ev[1], st);
         switch (amax_for(bc.rtot)) {
         case 5: rc = launch_solve<5>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
         case 9: rc = launch_solve<9>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
         case 11: rc = launch_solve<11>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
         default: rc = launch_solve<0>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
         }
+        cudaEventRecord(g_ev[2], st);
+        g_ev_pending = true;
         g_launch.launches += 2;
     }
     if (snbr) cudaFreeAsync(snbr, st);
