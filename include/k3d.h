@@ -155,7 +155,7 @@ int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, in
 
 /* Kernel launch facts for the last k3d_krige_slab on this thread (bench / tests).
    `launches` counts kernels launched so far: a slab takes one search and one solve kernel
-   per run of z-planes (one run unless the neighbour scratch would exceed 2 GB). */
+   per run of z-planes (one run unless the neighbour scratch would exceed 4 GB). */
 typedef struct K3dLaunchInfo {
     int32_t grid, block, smem_bytes, warps_per_cta; /* solve kernel */
     int32_t stage_capacity, list_capacity, launches;

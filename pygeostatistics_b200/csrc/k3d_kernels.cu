@@ -1563,16 +1563,19 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
                                   sc.smem_bytes));
 
     // neighbour lists travel from the search kernel to the solve kernel through global
-    // memory: the caller's arrays when given, else stream-ordered scratch, at most ~2 GB at
-    // a time (the slab is then processed in runs of z-planes)
+    // memory: the caller's arrays when given, else stream-ordered scratch, at most ~4 GB at
+    // a time (the slab is then processed in equal runs of z-planes)
     const size_t plane = (size_t)p->nx * p->ny;
     const size_t per_plane = plane * ((out->nbr_idx ? 0 : (size_t)p->ndmax * 4) + (out->nbr_cnt ? 0 : 4));
     int zstep = iz1 - iz0;
     if (per_plane > 0) {
-        const size_t cap = (size_t)2 << 30;
+        const size_t cap = (size_t)4 << 30;
         size_t fit = cap / per_plane;
         if (fit < 1) fit = 1;
-        if ((size_t)zstep > fit) zstep = (int)fit;
+        if ((size_t)zstep > fit) {
+            const int nruns = (int)(((size_t)zstep + fit - 1) / fit);
+            zstep = (zstep + nruns - 1) / nruns;
+        }
     }
     if (g_ev_dev != dev) { // per-thread timing events for k3d_last_launch
         for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&g_ev[i]));
