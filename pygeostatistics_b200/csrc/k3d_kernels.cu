@@ -132,6 +132,7 @@ __host__ __device__ inline int spw_off_sub(const SCfg &c) { return spw_off_octs(
 __host__ __device__ inline int spw_bytes(const SCfg &c) { return align16(spw_off_sub(c) + (c.cs >> 1) * 2); }
 // solve kernel
 //   CTA : [tri LUT u16 x ntri][block points per structure f64 x 3*nst*ndb]
+//         [round table u16 x warps*rounds_per_warp]
 //   warp: [P f64 x ntri]                        pristine bordered system (persists)
 //         [px,py,pz,va,ve f64 x ndp]            neighbours by matrix position
 //         [ut f64 x 3*nst*(ndp+ndb)]            their coordinates in structure space, then
@@ -140,7 +141,12 @@ __host__ __device__ inline int spw_bytes(const SCfg &c) { return align16(spw_off
 //         [pivot rows f64 x 2*urow][unode f64 x 3*nst]
 //         [part f64 x nsplit*napad]             block kriging: partial right-hand sides
 __host__ __device__ inline int b_off_udb(const BCfg &c) { return align16(c.ntri * 2); }
-__host__ __device__ inline int b_off_warp(const BCfg &c) { return align16(b_off_udb(c) + 3 * c.nst * c.ndb * 8); }
+__host__ __device__ inline int b_rounds_per_warp(const BCfg &c)
+{   // most rounds of 32 covariance items one node can publish: all pairs + the right-hand side
+    return ((c.ndp * (c.ndp - 1) / 2 + 31) >> 5) + c.nsplit * (c.napad >> 5);
+}
+__host__ __device__ inline int b_off_rtab(const BCfg &c) { return align16(b_off_udb(c) + 3 * c.nst * c.ndb * 8); }
+__host__ __device__ inline int b_off_warp(const BCfg &c) { return align16(b_off_rtab(c) + c.warps * b_rounds_per_warp(c) * 2); }
 __host__ __device__ inline int bpw_off_pos(const BCfg &c) { return align16(c.ntri * 8); }
 __host__ __device__ inline int bpw_off_ut(const BCfg &c) { return bpw_off_pos(c) + 5 * c.ndp * 8; }
 __host__ __device__ inline int bpw_off_ints(const BCfg &c) { return bpw_off_ut(c) + 3 * c.nst * (c.ndp + c.ndb) * 8; }
@@ -502,11 +508,18 @@ __device__ __forceinline__ int select_small(const K3dParams &P, double *keys, in
         const bool any = a0 || a1;
         const unsigned ch = any ? (use1 ? hi1 : hi0) : 0u;
         const unsigned mh = __reduce_max_sync(FULL, ch);
-        const unsigned cl = (any && ch == mh) ? (use1 ? lo1 : lo0) : 0u;
-        const unsigned ml = __reduce_max_sync(FULL, cl);
-        const unsigned cs = (any && ch == mh && cl == ml) ? (unsigned)(use1 ? s1 : s0) + 1u : 0u;
-        const unsigned ms = __reduce_max_sync(FULL, cs);
-        if (cs == ms && cs != 0u) {
+        bool mine = any && ch == mh;
+        if (__popc(__ballot_sync(FULL, mine)) > 1) { // equal high words (rare): low word, then slot
+            const unsigned cl = mine ? (use1 ? lo1 : lo0) : 0u;
+            const unsigned ml = __reduce_max_sync(FULL, cl);
+            mine = mine && cl == ml;
+            if (__popc(__ballot_sync(FULL, mine)) > 1) {
+                const unsigned cs = mine ? (unsigned)(use1 ? s1 : s0) + 1u : 0u;
+                const unsigned ms = __reduce_max_sync(FULL, cs);
+                mine = mine && cs == ms;
+            }
+        }
+        if (mine) {
             if (use1) v1 = false; else v0 = false;
         }
     };
@@ -938,6 +951,8 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
 
     __shared__ double s_exptab[32];  // 2^(j/32)
     __shared__ int s_job[20][6];     // per warp: npairs, npad, na, full, R, magic
+    __shared__ int s_nrounds[2];     // rounds of 32 covariance items published (by parity of tt)
+    unsigned short *s_rtab = (unsigned short *)(smem + b_off_rtab(cfg)); // (warp << 8) | round
     __shared__ double s_jloc[20][3]; // per warp: node location
 
     const Tile T = tile_of_block(P, in, iz0, iz1);
@@ -948,6 +963,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                  cz0 = P.zmn + T.zsb0 * P.zsiz;
 
     if (tid < 32) s_exptab[tid] = exp2((double)tid * 0.03125);
+    if (tid < 2) s_nrounds[tid] = 0;
     // ---- triangular index LUT: e -> (row<<8 | col), row >= col --------------
     for (int e = tid; e < cfg.ntri; e += nthreads) {
         int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
@@ -1082,22 +1098,28 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             }
             __syncwarp();
 
-            // publish this warp's covariance job for the pooled phase
-            if (lane == 0) {
+            // publish this warp's covariance job for the pooled phase: its parameters and
+            // one round-table entry per 32 work items
+            {
                 const int npairs = full ? (na * (na - 1)) >> 1 : nnew * na;
-                s_job[warp][0] = npairs;
-                s_job[warp][1] = (npairs + 31) & ~31;      // pairs, padded to whole rounds
-                s_job[warp][2] = na;
-                s_job[warp][3] = full ? 1 : 0;
-                s_job[warp][4] = R;
-                s_job[warp][5] = (65536 + na - 1) / na;
-                s_jloc[warp][0] = xloc; s_jloc[warp][1] = yloc; s_jloc[warp][2] = zloc;
+                const int npad = (npairs + 31) & ~31;  // pairs, padded to whole rounds
+                const int nr = (npad + nsplit * ((na + 31) & ~31)) >> 5;
+                int base = 0;
+                if (lane == 0) {
+                    s_job[warp][0] = npairs;
+                    s_job[warp][1] = npad;
+                    s_job[warp][2] = na;
+                    s_job[warp][3] = full ? 1 : 0;
+                    s_job[warp][4] = R;
+                    s_job[warp][5] = (65536 + na - 1) / na;
+                    s_jloc[warp][0] = xloc; s_jloc[warp][1] = yloc; s_jloc[warp][2] = zloc;
+                    base = atomicAdd(&s_nrounds[tt & 1], nr);
+                }
+                base = __shfl_sync(FULL, base, 0);
+                for (int r = lane; r < nr; r += 32) s_rtab[base + r] = (unsigned short)((warp << 8) | r);
             }
         }
-        if (!solve && lane == 0) {
-            s_job[warp][1] = 0;
-            s_job[warp][2] = 0;
-        }
+        if (tid == 0) s_nrounds[(tt + 1) & 1] = 0; // next node's counter: idle during this phase
         K3D_PHASE_BARRIER();
 
         // ---- 2. covariances of every node in flight, pooled over the CTA ---------------
@@ -1107,16 +1129,13 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         //   items [0, npairs)           sample-sample pairs: all, or those with a newcomer
         //   items [npad, npad + ...)    sample i against (a part of) the node's block points
         {
-            int next = 0; // warp that takes the next round of 32 items
-            for (int jw = 0; jw < cfg.warps; jw++) {
+            const int nrounds = s_nrounds[tt & 1];
+            for (int e = warp; e < nrounds; e += cfg.warps) {
+                const int ent = s_rtab[e];
+                const int jw = ent >> 8;
                 const int jnpad = s_job[jw][1], jna = s_job[jw][2];
                 const int jnapad = (jna + 31) & ~31;
-                const int jlen = jnpad + nsplit * jnapad;
-                int r0 = warp - next; // first round of this job that this warp takes
-                if (r0 < 0) r0 += cfg.warps;
-                next += jlen >> 5;
-                while (next >= cfg.warps) next -= cfg.warps;
-                if (jlen > 0) {
+                {
                     const int jnpairs = s_job[jw][0], jfull = s_job[jw][3], jR = s_job[jw][4];
                     const int magic = s_job[jw][5];
                     unsigned char *jb = smem + o_warp0 + jw * pwb;
@@ -1126,7 +1145,8 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     const double *jut = (const double *)(jb + o_ut);
                     const int *jnewpos = (const int *)(jb + o_ints) + ndp;
                     double *jpart = (double *)(jb + o_part);
-                    for (int w = (r0 << 5) + lane; w < jlen; w += cfg.warps << 5) {
+                    {
+                        const int w = ((ent & 255) << 5) + lane;
                         int p1 = 0, p2 = 0, nsub = 0, sub0 = 0;
                         const bool rhs = w >= jnpad;
                         int prt = 0;
