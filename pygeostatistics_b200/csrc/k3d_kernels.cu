@@ -1445,7 +1445,7 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
                                     {3, 4}, {12, 2}, {6, 4}};
     double best = -1.0;
     BCfg pick = *c;
-    int force_ctas = 0, force_warps = 0; // experiments: K3D_SOLVE_SHAPE="ctas,warps"
+    int force_ctas = 0, force_warps = 0; // tuning knob: K3D_SOLVE_SHAPE="ctas,warps"
     if (const char *e = getenv("K3D_SOLVE_SHAPE")) sscanf(e, "%d,%d", &force_ctas, &force_warps);
     for (unsigned i = 0; i < sizeof(shapes) / sizeof(shapes[0]); i++) {
         const int ctas = shapes[i][0], warps = shapes[i][1];
@@ -1589,7 +1589,9 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
     const size_t per_plane = plane * ((out->nbr_idx ? 0 : (size_t)p->ndmax * 4) + (out->nbr_cnt ? 0 : 4));
     int zstep = iz1 - iz0;
     if (per_plane > 0) {
-        const size_t cap = (size_t)4 << 30;
+        size_t cap = (size_t)4 << 30;
+        if (const char *e = getenv("K3D_SCRATCH_CAP_MB")) // tests: force several runs of planes
+            if (atoll(e) > 0) cap = (size_t)atoll(e) << 20;
         size_t fit = cap / per_plane;
         if (fit < 1) fit = 1;
         if ((size_t)zstep > fit) {

@@ -117,6 +117,24 @@ def test_scaled_configs_against_oracle(name, scale):
     assert n > 0.5 * len(k.estimation)
 
 
+def test_unordered_selection_path_and_plane_runs(monkeypatch):
+    """Production path: without the neighbour lists the kept set is not sorted (rows of the
+    system come in selection order) and the lists cross through pooled scratch; with a tiny
+    scratch cap the slab is processed in several runs of z-planes.  Estimates must still
+    match the oracle."""
+    par, data, sec = k3d_configs.config("c3", 0.2)
+    st, ores = oracle_run(par, data, sec)
+    k = gpu_run(par, data, sec, neighbours=False)
+    compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))), check_neighbours=False)
+    monkeypatch.setenv("K3D_SCRATCH_CAP_MB", "1")      # ~2 planes per run at this size
+    from pygeostatistics_b200 import _native
+    n0 = _native.last_launch()['launches']
+    k2 = gpu_run(par, data, sec, neighbours=False)
+    assert _native.last_launch()['launches'] - n0 > 4   # several search+solve pairs
+    compare(k2, st, ores, vmax=float(np.max(np.abs(data['v']))), check_neighbours=False)
+    assert np.allclose(k2.estimation, k.estimation, rtol=1e-11, atol=1e-12, equal_nan=True)
+
+
 # ---------------------------------------------------------------- full size, sampled nodes
 @pytest.mark.parametrize("name", ["c2", "c3", "c4"])
 def test_full_size_sampled_nodes_against_oracle(name):
