@@ -19,14 +19,20 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-I", os.path.join(ROOT, "include"), "--cudart", "shared"]
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, defines=()):
+    """`out` / `defines` build a tuning variant next to the product library (K3D_LIB selects
+    which one _native.py loads)."""
+    out = out or OUT
     newest = max(os.path.getmtime(f) for f in SRC + HDR + [os.path.abspath(__file__)])
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
-        return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + \
+        (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
+                out=args[0] if args else None, defines=args[1:]))

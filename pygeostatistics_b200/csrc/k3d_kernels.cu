@@ -96,6 +96,8 @@ struct BCfg {       // solve kernel
     int reuse;      // 1: keep the sample-sample covariance block between adjacent nodes
     int nsplit;     // block kriging: work items per sample of the right-hand side
     int napad;      // ndmax rounded up to a multiple of 32
+    int ustride;    // doubles per point in structure space: 4 per structure (x, y, z, pad)
+    int has_ext;    // 1: external-drift values of the neighbours are kept (ktype 2/3)
     int pw_bytes;   // per-warp shared bytes
     int smem_bytes; // total dynamic shared bytes
 };
@@ -134,25 +136,30 @@ __host__ __device__ inline int spw_bytes(const SCfg &c) { return align16(spw_off
 //   CTA : [tri LUT u16 x ntri][block points per structure f64 x 3*nst*ndb]
 //         [round table u16 x warps*rounds_per_warp]
 //   warp: [P f64 x ntri]                        pristine bordered system (persists)
-//         [px,py,pz,va,ve f64 x ndp]            neighbours by matrix position
-//         [ut f64 x 3*nst*(ndp+ndb)]            their coordinates in structure space, then
-//                                               the node's block points (columns ndp..)
-//         [pid,newpos,newid,cur i32 x ndp]      sample id by position / fill list / this node
-//         [pivot rows f64 x 2*urow][unode f64 x 3*nst]
+//         [px,py,pz,va(,ve) f64 x ndp]          neighbours by matrix position (ve: ktype 2/3)
+//         [ut f64 x ustride*(ndp+ndb)]          their coordinates in structure space (one
+//                                               record of nst x (x, y, z, pad) per point), then
+//                                               the node's block points (records ndp..)
+//         [pid,newid i32 x ndp][newpos u8 x ndp] sample id by position / fill list
+//         [pivot rows f64 x 2*urow]              the node's structure-space record (unode,
+//                                               ustride doubles, set-up phase only) shares it
 //         [part f64 x nsplit*napad]             block kriging: partial right-hand sides
-__host__ __device__ inline int b_off_udb(const BCfg &c) { return align16(c.ntri * 2); }
+__host__ __device__ inline int b_off_udb(const BCfg &c) { return align16(c.ntri * 2); } // 16-byte aligned records
 __host__ __device__ inline int b_rounds_per_warp(const BCfg &c)
 {   // most rounds of 32 covariance items one node can publish: all pairs + the right-hand side
     return ((c.ndp * (c.ndp - 1) / 2 + 31) >> 5) + c.nsplit * (c.napad >> 5);
 }
-__host__ __device__ inline int b_off_rtab(const BCfg &c) { return align16(b_off_udb(c) + 3 * c.nst * c.ndb * 8); }
+__host__ __device__ inline int b_off_rtab(const BCfg &c) { return align16(b_off_udb(c) + c.ustride * c.ndb * 8); }
 __host__ __device__ inline int b_off_warp(const BCfg &c) { return align16(b_off_rtab(c) + c.warps * b_rounds_per_warp(c) * 2); }
 __host__ __device__ inline int bpw_off_pos(const BCfg &c) { return align16(c.ntri * 8); }
-__host__ __device__ inline int bpw_off_ut(const BCfg &c) { return bpw_off_pos(c) + 5 * c.ndp * 8; }
-__host__ __device__ inline int bpw_off_ints(const BCfg &c) { return bpw_off_ut(c) + 3 * c.nst * (c.ndp + c.ndb) * 8; }
-__host__ __device__ inline int bpw_off_rows(const BCfg &c) { return align16(bpw_off_ints(c) + 4 * c.ndp * 4); }
-__host__ __device__ inline int bpw_off_unode(const BCfg &c) { return bpw_off_rows(c) + 2 * c.urow * 8; }
-__host__ __device__ inline int bpw_off_part(const BCfg &c) { return bpw_off_unode(c) + 3 * c.nst * 8; }
+__host__ __device__ inline int bpw_off_ut(const BCfg &c) { return bpw_off_pos(c) + (4 + c.has_ext) * c.ndp * 8; }
+__host__ __device__ inline int bpw_off_ints(const BCfg &c) { return bpw_off_ut(c) + c.ustride * (c.ndp + c.ndb) * 8; }
+__host__ __device__ inline int bpw_off_rows(const BCfg &c) { return align16(bpw_off_ints(c) + 9 * c.ndp); }
+__host__ __device__ inline int bpw_off_part(const BCfg &c)
+{
+    const int rows = 2 * c.urow > c.ustride ? 2 * c.urow : c.ustride;
+    return bpw_off_rows(c) + rows * 8;
+}
 __host__ __device__ inline int bpw_bytes(const BCfg &c)
 {
     return align16(bpw_off_part(c) + (c.nsplit > 1 ? c.nsplit * c.napad * 8 : 0));
@@ -177,23 +184,69 @@ __device__ __forceinline__ double sqdist_exact(double dx, double dy, double dz,
     return s;
 }
 
+// explicit shared-window accesses for the hottest loop (32-bit addresses, no generic-pointer
+// arithmetic in the instruction stream)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_u16(uint32_t a)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return (int)v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// polynomial and reduction constants of exp_neg, kept in the constant bank so that every
+// DFMA takes its coefficient as an operand
+__constant__ double k_expc[10] = {
+    46.166241308446828384,       // 32 / ln 2
+    -0.021660849390173098,       // -ln2/32 high part (20 trailing zero bits)
+    -2.325192846878874e-12,      // -ln2/32 low part
+    1.98412698412698412698e-04,  // 1/5040
+    1.38888888888888888889e-03,  // 1/720
+    8.33333333333333333333e-03,  // 1/120
+    4.16666666666666666667e-02,  // 1/24
+    1.66666666666666666667e-01,  // 1/6
+    6755399441055744.0,          // 1.5 * 2^52
+    0.0};
+
 // exp(x) for x <= 0 to ~1 ulp: x = (32 k + j) ln2/32 + r, exp(x) = 2^k * 2^(j/32) * e^r with
 // |r| <= ln2/64 (degree-6 polynomial) and 2^(j/32) from a 32-entry shared-memory table.
 // About half the instructions of the library exp; no special cases are needed on this
 // domain (results below 2^-1000 are flushed to zero).
 __device__ __forceinline__ double exp_neg(double x, const double *__restrict__ tab)
 {
-    const double magic = 6755399441055744.0; // 1.5 * 2^52
-    double kd = fma(x, 46.166241308446828384, magic); // 32 / ln 2
+    const double magic = k_expc[8];
+    double kd = fma(x, k_expc[0], magic);
     const int ki = __double2loint(kd);
     kd -= magic;
-    double r = fma(kd, -0.021660849390173098, x); // ln2/32 high part (20 trailing zero bits)
-    r = fma(kd, -2.325192846878874e-12, r);       // low part
-    double p = 1.98412698412698412698e-04;  // 1/5040
-    p = fma(p, r, 1.38888888888888888889e-03);
-    p = fma(p, r, 8.33333333333333333333e-03);
-    p = fma(p, r, 4.16666666666666666667e-02);
-    p = fma(p, r, 1.66666666666666666667e-01);
+    double r = fma(kd, k_expc[1], x);
+    r = fma(kd, k_expc[2], r);
+    double p = k_expc[3];
+    p = fma(p, r, k_expc[4]);
+    p = fma(p, r, k_expc[5]);
+    p = fma(p, r, k_expc[6]);
+    p = fma(p, r, k_expc[7]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = p * r; // e^r - 1
@@ -222,6 +275,26 @@ __device__ __forceinline__ double sqrt_pos(double a)
 // distances h2[s] = (h/a)^2 (h^2 for a power structure).  Inlined at exactly ONE call
 // site (the assembly work loop): the transcendental code is large and the instruction
 // cache is small.
+// one structure's term of cova3 (krige3d.py:856-874) at squared scaled distance h2
+__device__ __forceinline__ double cova_term(const K3dParams &P, const KPrep &Q, int s, double h2,
+                                            const double *__restrict__ exptab)
+{
+    const double c = Q.cc[s];
+    const int it = Q.it[s];
+    if (it == 1) {
+        const double hr = sqrt_pos(h2);
+        const double v = c * (1.0 - hr * (1.5 - 0.5 * h2));
+        return h2 < 1.0 ? v : 0.0;
+    } else if (it == 2) {
+        return c * exp_neg(-3.0 * sqrt_pos(h2), exptab);
+    } else if (it == 3) {
+        return c * exp_neg(-3.0 * h2, exptab);
+    } else if (it == 4) {
+        return P.maxcov - c * pow(sqrt(h2), Q.aa[s]);
+    }
+    return c * cos(sqrt(h2) * 3.141592653589793);
+}
+
 __device__ __forceinline__ double cova_from_h2(const K3dParams &P, const KPrep &Q,
                                                const double (&h2v)[K3D_MAXNST],
                                                const double *__restrict__ exptab)
@@ -231,38 +304,23 @@ __device__ __forceinline__ double cova_from_h2(const K3dParams &P, const KPrep &
     double cova = 0.0;
 #pragma unroll 1
     for (int s = 0; s < P.nst; s++) {
-        {
-            const double h2 = s == 0 ? h2v[0] : s == 1 ? h2v[1] : s == 2 ? h2v[2] : h2v[3];
-            const double c = Q.cc[s];
-            const int it = Q.it[s];
-            if (it == 1) {
-                if (h2 < 1.0) {
-                    double hr = sqrt_pos(h2);
-                    cova += c * (1.0 - hr * (1.5 - 0.5 * h2));
-                }
-            } else if (it == 2) {
-                cova += c * exp_neg(-3.0 * sqrt_pos(h2), exptab);
-            } else if (it == 3) {
-                cova += c * exp_neg(-3.0 * h2, exptab);
-            } else if (it == 4) {
-                cova += P.maxcov - c * pow(sqrt(h2), Q.aa[s]);
-            } else {
-                cova += c * cos(sqrt(h2) * 3.141592653589793);
-            }
-        }
+        const double h2 = s == 0 ? h2v[0] : s == 1 ? h2v[1] : s == 2 ? h2v[2] : h2v[3];
+        cova += cova_term(P, Q, s, h2, exptab);
     }
     return cova;
 }
 
-// u = rs[s] * (x,y,z) for every structure, written at [..][idx] of a [3*nst][stride] array
+// u = rs[s] * (x,y,z) for every structure, written as record idx (4 doubles per structure:
+// x, y, z, pad; records `stride` doubles apart)
 __device__ __forceinline__ void transform_point(const K3dParams &P, const KPrep &Q, double x,
                                                 double y, double z, double *u, int stride, int idx)
 {
+    double *o = u + idx * stride;
     for (int s = 0; s < P.nst; s++) {
         const double *r = Q.rs[s];
-        u[(3 * s + 0) * stride + idx] = r[0] * x + r[1] * y + r[2] * z;
-        u[(3 * s + 1) * stride + idx] = r[3] * x + r[4] * y + r[5] * z;
-        u[(3 * s + 2) * stride + idx] = r[6] * x + r[7] * y + r[8] * z;
+        o[4 * s + 0] = r[0] * x + r[1] * y + r[2] * z;
+        o[4 * s + 1] = r[3] * x + r[4] * y + r[5] * z;
+        o[4 * s + 2] = r[6] * x + r[7] * y + r[8] * z;
     }
 }
 // out-of-line copy for the rarely executed call sites
@@ -317,7 +375,7 @@ template <int AMAX> struct RegSolve {
     {
         if constexpr (AP >= 0) {
             if (4 * AP <= R) { // uniform: does this row block exist in the system?
-#pragma unroll 1
+#pragma unroll // (rolled, the loop control and row addressing cost 10 % of the kernel)
                 for (int q = 3; q >= 0; q--) {
                     const int M = 4 * AP + q;
                     if (M > R || M < 2) continue;
@@ -921,7 +979,9 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
 // SOLVE kernel: kriging system assembly (krige3d.py:470-583, 748-801, 838-875), solve and
 // estimate (krige3d.py:590-614) from the neighbour lists of the search kernel
 // ---------------------------------------------------------------------------
-template <int AMAX>
+// BLOCK: block kriging (ndb > 1), whose right-hand side averages over the block points;
+// point kriging takes a leaner covariance loop driven by per-warp work-item lists.
+template <int AMAX, bool BLOCK>
 __global__ void __launch_bounds__(AMAX == 5 ? 256 : 640, AMAX == 5 ? K3D_SMALL_CTAS : 1)
 k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
                  const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
@@ -940,13 +1000,14 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     unsigned char *wbase = smem + o_warp0 + warp * pwb;
     double *Pm = (double *)wbase;
     double *px = (double *)(wbase + o_pos);
-    double *py = px + ndp, *pz = py + ndp, *va = pz + ndp, *ve = va + ndp;
+    double *py = px + ndp, *pz = py + ndp, *va = pz + ndp, *ve = va + ndp; // ve: has_ext only
     double *ut = (double *)(wbase + o_ut);
     int *pid = (int *)(wbase + o_ints);
-    int *newpos = pid + ndp, *newid = newpos + ndp, *cur = newid + ndp;
-    const int ucols = ndp + cfg.ndb; // columns of ut: neighbours by position, then block points
+    int *newid = pid + ndp;
+    unsigned char *newpos = (unsigned char *)(newid + ndp);
+    const int ustride = cfg.ustride; // records of ut: neighbours by position, then block points
     double *rows = (double *)(wbase + bpw_off_rows(cfg));
-    double *unode = (double *)(wbase + bpw_off_unode(cfg));
+    double *unode = rows; // set-up phase only; the pivot rows are live during the solve
     double *part = (double *)(wbase + o_part);
 
     __shared__ double s_exptab[32];  // 2^(j/32)
@@ -974,7 +1035,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     // ---- block discretisation offsets in every structure's coordinates -------
     for (int j = tid; j < P.ndb; j += nthreads)
         transform_point_cold(P, Q, in.dbxyz[j], in.dbxyz[P.ndb + j], in.dbxyz[2 * P.ndb + j],
-                             udb, P.ndb, j);
+                             udb, ustride, j);
     __syncthreads();
 
     const double *db = in.dbxyz;
@@ -1021,8 +1082,6 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         }
         if (live) {
             na = cnt[o];
-            for (int i = lane; i < na; i += 32) cur[i] = nbr[o * P.ndmax + i];
-            __syncwarp();
         }
 
         bool solve = false;
@@ -1052,7 +1111,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             bool full = true;
             if (cfg.reuse && nprev == na && na <= 32) {
                 int pos = -1;
-                const int myid = lane < na ? cur[lane] : -1;
+                const int myid = lane < na ? nbr[o * P.ndmax + lane] : -1;
                 for (int p = 0; p < na; p++)
                     if (pid[p] == myid) pos = p;
                 if (lane >= na) pos = -2;
@@ -1066,15 +1125,15 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         unsigned freem = ~used & (na == 32 ? 0xffffffffu : ((1u << na) - 1u));
                         const int r = __popc(unm & ltm);
                         for (int k = 0; k < r; k++) freem &= freem - 1u;
-                        newpos[r] = __ffs(freem) - 1;
+                        newpos[r] = (unsigned char)(__ffs(freem) - 1);
                         newid[r] = myid;
                     }
                 }
             }
             if (full) { // positions = list order
                 for (int i = lane; i < na; i += 32) {
-                    newpos[i] = i;
-                    newid[i] = cur[i];
+                    newpos[i] = (unsigned char)i;
+                    newid[i] = nbr[o * P.ndmax + i];
                 }
             }
             __syncwarp();
@@ -1085,16 +1144,20 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 px[pos] = x; py[pos] = y; pz[pos] = z;
                 const double v = in.sv[g], e = has_ext ? in.ssec[g] : 0.0;
                 va[pos] = (P.ktype == 0) ? v - P.skmean : (P.ktype == 2 ? v - e : v);
-                ve[pos] = e;
-                transform_point(P, Q, x - cx0, y - cy0, z - cz0, ut, ucols, pos);
+                if (has_ext) ve[pos] = e;
+                transform_point(P, Q, x - cx0, y - cy0, z - cz0, ut, ustride, pos);
             }
             // the node and its block points in every structure's coordinates (columns ndp..)
             if (lane == 0)
                 transform_point_cold(P, Q, xloc - cx0, yloc - cy0, zloc - cz0, unode, 1, 0);
             __syncwarp();
-            for (int k = lane; k < 3 * P.nst * P.ndb; k += 32) {
-                const int row = k / P.ndb, j = k - row * P.ndb;
-                ut[row * ucols + ndp + j] = unode[row] + udb[row * P.ndb + j];
+            if constexpr (BLOCK) {
+                for (int k = lane; k < ustride * P.ndb; k += 32) {
+                    const int j = k / ustride, row = k - j * ustride;
+                    ut[(ndp + j) * ustride + row] = unode[row] + udb[j * ustride + row];
+                }
+            } else {
+                if (lane < ustride) ut[ndp * ustride + lane] = unode[lane] + udb[lane];
             }
             __syncwarp();
 
@@ -1102,17 +1165,28 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             // one round-table entry per 32 work items
             {
                 const int npairs = full ? (na * (na - 1)) >> 1 : nnew * na;
-                const int npad = (npairs + 31) & ~31;  // pairs, padded to whole rounds
-                const int nr = (npad + nsplit * ((na + 31) & ~31)) >> 5;
+                int nr;
+                if constexpr (BLOCK) {
+                    const int npad = (npairs + 31) & ~31;  // pairs, padded to whole rounds
+                    nr = (npad + nsplit * ((na + 31) & ~31)) >> 5;
+                    if (lane == 0) {
+                        s_job[warp][0] = npairs;
+                        s_job[warp][1] = npad;
+                        s_job[warp][2] = na;
+                        s_job[warp][3] = full ? 1 : 0;
+                        s_job[warp][5] = (65536 + na - 1) / na;
+                        s_jloc[warp][0] = xloc; s_jloc[warp][1] = yloc; s_jloc[warp][2] = zloc;
+                    }
+                } else {
+                    // pair rounds: one per newcomer (lane = the other position), or the
+                    // whole triangle 32 pairs at a time; then the right-hand side
+                    const int npr = full ? (npairs + 31) >> 5 : nnew;
+                    nr = npr + ((na + 31) >> 5);
+                    if (lane == 0) s_job[warp][0] = R | (na << 8) | (npr << 16) | (full ? 1 << 24 : 0);
+                }
                 int base = 0;
                 if (lane == 0) {
-                    s_job[warp][0] = npairs;
-                    s_job[warp][1] = npad;
-                    s_job[warp][2] = na;
-                    s_job[warp][3] = full ? 1 : 0;
-                    s_job[warp][4] = R;
-                    s_job[warp][5] = (65536 + na - 1) / na;
-                    s_jloc[warp][0] = xloc; s_jloc[warp][1] = yloc; s_jloc[warp][2] = zloc;
+                    if constexpr (BLOCK) s_job[warp][4] = R;
                     base = atomicAdd(&s_nrounds[tt & 1], nr);
                 }
                 base = __shfl_sync(FULL, base, 0);
@@ -1130,6 +1204,55 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         //   items [npad, npad + ...)    sample i against (a part of) the node's block points
         {
             const int nrounds = s_nrounds[tt & 1];
+            if constexpr (!BLOCK) {
+                // point kriging: one item = the covariance between two records of the job's
+                // structure-space table (krige3d.py:748-801, 838-875); a round is either 32
+                // sample pairs or the right-hand side of up to 32 samples (record ndp = node)
+                const uint32_t a_rtab = smem_u32(s_rtab), a_w0 = smem_u32(smem + o_warp0),
+                               a_job = smem_u32(&s_job[0][0]), a_tri = smem_u32(tri);
+                const int o_newpos = o_ints + 8 * ndp;
+                for (int e = warp; e < nrounds; e += cfg.warps) {
+                    const int ent = lds_u16(a_rtab + 2 * e);
+                    const int jw = ent >> 8, r = ent & 255;
+                    const uint32_t jb = a_w0 + jw * pwb;
+                    const int job = lds_s32(a_job + jw * (int)sizeof(s_job[0]));
+                    const int jR = job & 255, jna = (job >> 8) & 255, npr = (job >> 16) & 255;
+                    // idle lanes repeat the last item of their kind (same value, same place)
+                    const bool rhs = r >= npr;
+                    int p1, p2r;
+                    if (rhs) {
+                        p1 = min(((r - npr) << 5) + lane, jna - 1);
+                        p2r = ndp;
+                    } else if (job >> 24) {
+                        const int w = min((r << 5) + lane, ((jna * (jna - 1)) >> 1) - 1);
+                        const int rc = lds_u16(a_tri + 2 * w);
+                        p1 = rc & 255;
+                        p2r = (rc >> 8) + 1;
+                    } else {
+                        int pn;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pn) : "r"(jb + o_newpos + r));
+                        const int q = min(lane, jna - 1);
+                        p1 = min(pn, q);
+                        p2r = max(pn, q);
+                    }
+                    uint32_t a1 = jb + o_ut + p1 * (ustride << 3);
+                    uint32_t a2 = jb + o_ut + p2r * (ustride << 3);
+                    double c = 0.0;
+                    bool zero = false;
+#pragma unroll 1
+                    for (int st = 0; st < P.nst; st++, a1 += 32, a2 += 32) {
+                        const double2 u = lds_f64x2(a1), v = lds_f64x2(a2);
+                        const double uz = lds_f64(a1 + 16), vz = lds_f64(a2 + 16);
+                        const double dx = u.x - v.x, dy = u.y - v.y, dz = uz - vz;
+                        const double h2 = dx * dx + dy * dy + dz * dz;
+                        if (st == 0) zero = h2 < Q.eps0s;
+                        c += cova_term(P, Q, st, h2, s_exptab);
+                    }
+                    if (zero) c = P.maxcov; // krige3d.py:853-855
+                    const int ri = jR - p1;
+                    sts_f64(jb + (pk(ri, rhs ? 1 : jR - p2r) << 3), c);
+                }
+            } else {
             for (int e = warp; e < nrounds; e += cfg.warps) {
                 const int ent = s_rtab[e];
                 const int jw = ent >> 8;
@@ -1143,7 +1266,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     const double *jpx = (const double *)(jb + o_pos);
                     const double *jpy = jpx + ndp, *jpz = jpy + ndp;
                     const double *jut = (const double *)(jb + o_ut);
-                    const int *jnewpos = (const int *)(jb + o_ints) + ndp;
+                    const unsigned char *jnewpos = (const unsigned char *)((const int *)(jb + o_ints) + 2 * ndp);
                     double *jpart = (double *)(jb + o_part);
                     {
                         const int w = ((ent & 255) << 5) + lane;
@@ -1178,12 +1301,13 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         double acc = 0.0;
                         for (int sub = sub0; sub < sub0 + nsub; sub++, p2++) {
                             double h2v[K3D_MAXNST] = {0.0, 0.0, 0.0, 0.0};
+                            const double *u1 = jut + p1 * ustride, *u2 = jut + p2 * ustride;
 #pragma unroll
                             for (int st = 0; st < K3D_MAXNST; st++) {
                                 if (st < P.nst) {
-                                    const double *u = jut + 3 * st * ucols;
-                                    const double dx = u[p1] - u[p2], dy = u[ucols + p1] - u[ucols + p2],
-                                                 dz = u[2 * ucols + p1] - u[2 * ucols + p2];
+                                    const double dx = u1[4 * st] - u2[4 * st],
+                                                 dy = u1[4 * st + 1] - u2[4 * st + 1],
+                                                 dz = u1[4 * st + 2] - u2[4 * st + 2];
                                     h2v[st] = dx * dx + dy * dy + dz * dz;
                                 }
                             }
@@ -1208,6 +1332,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         }
                     }
                 }
+            }
             }
         }
         K3D_PHASE_BARRIER();
@@ -1425,6 +1550,8 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
     c->ndp = (p->ndmax + 3) & ~3;
     c->nst = p->nst;
     c->ndb = p->ndb;
+    c->ustride = 4 * p->nst;
+    c->has_ext = (p->ktype == 2 || p->ktype == 3) ? 1 : 0;
     const int amax = amax_for(c->rtot);
     c->urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c->rtot;
     c->reuse = amax > 0 ? 1 : 0;
@@ -1494,17 +1621,26 @@ int scratch_pool(int dev, cudaMemPool_t *pool)
     return K3D_OK;
 }
 
+template <int AMAX, bool BLOCK>
+int launch_solve2(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
+                  int iz0, int iz1, const int32_t *nbr, int32_t *cnt, const BCfg &c,
+                  long long ntiles, cudaStream_t st)
+{
+    CUDA_TRY(cudaFuncSetAttribute(k3d_solve_kernel<AMAX, BLOCK>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+    k3d_solve_kernel<AMAX, BLOCK><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(
+        *p, *q, *in, *out, iz0, iz1, nbr, cnt, c);
+    CUDA_TRY(cudaGetLastError());
+    return K3D_OK;
+}
+
 template <int AMAX>
 int launch_solve(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
                  int iz0, int iz1, const int32_t *nbr, int32_t *cnt, const BCfg &c,
                  long long ntiles, cudaStream_t st)
 {
-    CUDA_TRY(cudaFuncSetAttribute(k3d_solve_kernel<AMAX>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
-    k3d_solve_kernel<AMAX><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(
-        *p, *q, *in, *out, iz0, iz1, nbr, cnt, c);
-    CUDA_TRY(cudaGetLastError());
-    return K3D_OK;
+    return p->ndb > 1 ? launch_solve2<AMAX, true>(p, q, in, out, iz0, iz1, nbr, cnt, c, ntiles, st)
+                      : launch_solve2<AMAX, false>(p, q, in, out, iz0, iz1, nbr, cnt, c, ntiles, st);
 }
 
 } // namespace

@@ -47,9 +47,9 @@ def _pinned_array(numel, dtype):
         entry = [torch.empty(max(numel, 1), dtype=dtype, pin_memory=True), None]
         _PINNED.append(entry)
         if len(_PINNED) > 16:  # drop idle buffers, oldest first
-            idle = [e for e in _PINNED[:-1] if e[1] is None or e[1]() is None]
-            for e in idle[:len(_PINNED) - 16]:
-                _PINNED.remove(e)
+            idle = [id(e) for e in _PINNED[:-1] if e[1] is None or e[1]() is None]
+            drop = set(idle[:len(_PINNED) - 16])
+            _PINNED[:] = [e for e in _PINNED if id(e) not in drop]  # (list.remove would compare tensors)
     view = entry[0][:numel]
     arr = view.numpy()
     entry[1] = weakref.ref(arr)
