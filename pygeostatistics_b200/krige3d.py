@@ -283,7 +283,7 @@ class Krige3d(object):
         s.rotmat = self.rotmat[-1]
         s.radsqd = self.radsqd
         s.noct = self.noct
-        s.setup()
+        s.setup(self._device())
         s.pickup(self._device())
         self.searcher = s
         self.vr = s.vr  # sorted by super block (krige3d.py:690)
@@ -381,12 +381,10 @@ class Krige3d(object):
     def _host_inputs(self):
         """Pinned host copies of everything the kernel reads."""
         s = self.searcher
-        sec = self.vr[self.property_name[1]] if (self.ktype in (2, 3)) else None
+        c = s.cols  # contiguous sorted columns
         host = dict(
-            sx=np.ascontiguousarray(self.vr['x']), sy=np.ascontiguousarray(self.vr['y']),
-            sz=np.ascontiguousarray(self.vr['z']),
-            sv=np.ascontiguousarray(self.vr[self.property_name[0]]),
-            ssec=None if sec is None else np.ascontiguousarray(sec),
+            sx=c['x'], sy=c['y'], sz=c['z'], sv=c[self.property_name[0]],
+            ssec=c[self.property_name[1]] if (self.ktype in (2, 3)) else None,
             sbstart=s.sbstart, runs=s.runs.reshape(-1), nodex0=s.nodex0, nodey0=s.nodey0,
             nodez0=s.nodez0,
             dbxyz=np.ascontiguousarray(np.concatenate([self.xdb, self.ydb, self.zdb])))
@@ -439,6 +437,23 @@ class Krige3d(object):
                 ext.shape[0], self.nx * self.ny * self.nz))
         return torch.from_numpy(np.array(ext, dtype=np.float64, copy=True))
 
+    _COPY_STREAMS = {}
+
+    def _copy_stream(self):
+        dev = self._device()
+        if dev not in Krige3d._COPY_STREAMS:
+            Krige3d._COPY_STREAMS[dev] = torch.cuda.Stream(dev)
+        return Krige3d._COPY_STREAMS[dev]
+
+    def _plane_runs(self, iz0, iz1, target=4):
+        """[iz0, iz1) cut into about `target` runs of z-planes at super-block boundaries (a
+        run that splits a super block would shorten the walks of its tiles)."""
+        starts = [int(z) for z in self.searcher.nodez0 if iz0 < z < iz1]
+        want = [iz0 + (iz1 - iz0) * j // target for j in range(1, target)]
+        cuts = sorted({min(starts, key=lambda z: abs(z - w)) for w in want}) if starts else []
+        edges = [iz0] + cuts + [iz1]
+        return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
     # ------------------------------------------------------------------ the driver
     def prepare(self):
         """Everything krige3d.py:255-282 does before the node loop."""
@@ -486,16 +501,40 @@ class Krige3d(object):
         ext_slab = None if ext is None else ext[iz0 * plane: iz1 * plane].pin_memory()
         d = self._upload(host, ext_slab)
         out = self._alloc_outputs(nodes, neighbours)
-        if nodes > 0:
-            self._launch(P, d, iz0, iz1, out)
-        if world > 1:
-            out = {k: gather_slabs(v, ranges, plane * (self.ndmax if k == 'nbr_idx' else 1), group)
-                   for k, v in out.items()}
         res = {}
-        for k, v in out.items():
-            view, arr = _pinned_array(v.numel(), v.dtype)
-            view.copy_(v, non_blocking=True)
-            res[k] = arr
+        if world == 1 and nodes > 0:
+            # one rank: the slab goes in a few runs of z-planes (cut where super blocks
+            # end), and the device-to-host copy of a run overlaps the kernels of the next
+            dev = self._device()
+            main, side = torch.cuda.current_stream(dev), self._copy_stream()
+            pinned = {k: _pinned_array(v.numel(), v.dtype) for k, v in out.items()}
+            for za, zb in self._plane_runs(iz0, iz1):
+                a, b = (za - iz0) * plane, (zb - iz0) * plane
+                width = lambda k: self.ndmax if k == 'nbr_idx' else 1
+                dd = dict(d)
+                if d['extgrid'] is not None:
+                    dd['extgrid'] = d['extgrid'][a:b]
+                self._launch(P, dd, za, zb, {k: v[a * width(k): b * width(k)] for k, v in out.items()})
+                done = torch.cuda.Event()
+                done.record(main)
+                side.wait_event(done)
+                with torch.cuda.stream(side):
+                    for k, v in out.items():
+                        pinned[k][0][a * width(k): b * width(k)].copy_(
+                            v[a * width(k): b * width(k)], non_blocking=True)
+            side.synchronize()
+            main.wait_stream(side)
+            res = {k: pv[1] for k, pv in pinned.items()}
+        else:
+            if nodes > 0:
+                self._launch(P, d, iz0, iz1, out)
+            if world > 1:
+                out = {k: gather_slabs(v, ranges, plane * (self.ndmax if k == 'nbr_idx' else 1), group)
+                       for k, v in out.items()}
+            for k, v in out.items():
+                view, arr = _pinned_array(v.numel(), v.dtype)
+                view.copy_(v, non_blocking=True)
+                res[k] = arr
         torch.cuda.synchronize(self._device())
         self.timings['krige_s'] = time.time() - t0
         self.timings['total_s'] = time.time() - t0 + self.timings.get('setup_s', 0.0)

@@ -15,7 +15,8 @@ import pytest
 import k3d_configs
 from pygeostatistics_b200 import (Krige3d, SpatialData, SuperBlockSearcher, slab_ranges,
                                   write_gslib_grid, _native)
-from pygeostatistics_b200.super_block import template_runs
+from pygeostatistics_b200.super_block import (template_runs, runs_from_offsets, bins_left,
+                                                _edges_sample)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -138,6 +139,26 @@ def test_host_setup_matches_reference_state(golden_dir):
     assert np.array_equal(back, m)
     key = runs[:, 3].astype(int) * 10000 + runs[:, 2].astype(int) * 100 + runs[:, 0]
     assert np.all(np.diff(key) > 0)
+    # the device route hands over offset lists instead of the mask: same runs
+    s.set_template_offsets(tm[0], tm[1], tm[2])
+    assert np.array_equal(s.runs, runs) and s.nsbtosr == tm.shape[1]
+    assert np.array_equal(runs_from_offsets(tm[0][::-1], tm[1][::-1], tm[2][::-1]), runs)
+
+
+def test_bins_left_equals_searchsorted():
+    """The arithmetic binning is np.searchsorted(edges, x) - 1 exactly (super_block.py:114-124),
+    also for coordinates ON an edge, outside the network, and for arange's rounded edges."""
+    rng = np.random.default_rng(11)
+    for mn, siz, n in ((0.5 * 5.12, 5.12, 50), (200.0, 400.0, 49), (0.05, 0.1, 37),
+                       (-3.3, 1.0 / 3.0, 20), (1e6 + 0.7, 0.7, 1)):
+        e = _edges_sample(mn, siz, n)
+        x = np.concatenate([rng.uniform(e[0] - 3 * siz, e[-1] + 3 * siz, 20000), e,
+                            np.nextafter(e, -np.inf), np.nextafter(e, np.inf),
+                            [e[0] - 1e30, e[-1] + 1e30]])
+        assert np.array_equal(bins_left(e, x), np.searchsorted(e, x) - 1)
+    e = np.array([0.0, 1.0, 1.5, 7.0, 7.25, 30.0])  # irregular: falls back to the search
+    x = rng.uniform(-2, 35, 1000)
+    assert np.array_equal(bins_left(e, x), np.searchsorted(e, x) - 1)
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -231,3 +252,20 @@ def test_pinned_result_pool_keeps_arrays_private(monkeypatch):
         gc.collect()
     assert len(k3._PINNED) <= 17
     assert all(any(e[1] is not None and e[1]() is a for e in k3._PINNED) for a in keep)
+
+
+def test_plane_runs_cut_at_super_block_boundaries():
+    """kt3d() pipelines the slab in a few runs of z-planes: they tile [iz0, iz1) exactly and
+    every inner cut is the first plane of a super block."""
+    from pygeostatistics_b200 import Krige3d
+
+    class _S(object):
+        nodez0 = np.array([0, 5, 10, 15, 20, 26, 31, 36, 41, 46, 51, 56, 61, 64])
+    k = Krige3d.__new__(Krige3d)
+    k.searcher = _S()
+    for iz0, iz1 in ((0, 64), (10, 13), (0, 1), (16, 48), (3, 64), (20, 26)):
+        runs = k._plane_runs(iz0, iz1)
+        assert runs[0][0] == iz0 and runs[-1][1] == iz1 and len(runs) <= 4
+        assert all(a[1] == b[0] for a, b in zip(runs[:-1], runs[1:]))
+        assert all(a < b for a, b in runs)
+        assert all(b in _S.nodez0 for _, b in runs[:-1])
