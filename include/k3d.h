@@ -136,6 +136,29 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
                    const K3dOutputs *out, void *stream);
 
 /*
+ * Estimation at listed locations instead of grid nodes: cross-validation (`option` 1,
+ * the locations are the data themselves) and jackknife (`option` 2, the records of
+ * `jackfl`), krige3d.py:310-332 + 359-363 (the reference reads no file there and crashes;
+ * semantics per its own acceptance loop and gslib_help/kt3d_help.md:20-27).
+ * The locations are grouped by the super block they fall in (super_block.py:319-346),
+ * stable within a block; results are indexed by position in these arrays.
+ */
+typedef struct K3dPoints {
+    int64_t npts;
+    const double *x, *y, *z;  /* device: locations, sorted by super block */
+    const double *ext;        /* device: external-drift value at each location (ktype 2/3) or NULL */
+    const int32_t *start;     /* device: [nxsup*nysup*nzsup + 1] first location of each super block */
+    int32_t exclude_coincident; /* 1: samples with |dx|+|dy|+|dz| < eps of the location are
+                                   not used (krige3d.py:359-363, option != 0) */
+    int32_t _pad;
+} K3dPoints;
+
+/* Same path as k3d_krige_slab for the locations of `pts`; K3dInputs.extgrid is not read,
+   every K3dOutputs array has pts->npts (x ndmax) elements.  Asynchronous on `stream`. */
+int k3d_krige_points(const K3dParams *p, const K3dInputs *in, const K3dPoints *pts,
+                     const K3dOutputs *out, void *stream);
+
+/*
  * Builds the search template mask on the device: mask[((i*ny2)+j)*nz2+k] = 1 when
  * offset (i-(nxsup-1), j-(nysup-1), k-(nzsup-1)) must be searched; n?2 = 2*n?sup-1.
  * Replaces func_pickup (super_block.py:226-265).  `mask` is a device pointer.

@@ -352,37 +352,41 @@ void orc_right_side(const OrcParams *p, int na, int neq, const double *xa,
  * :470-614 (_many_samples) with repairs D6 (drift rows), D7/D8 (external variable),
  * D10 (itrend), D15 (na==0 -> unestimated).
  */
-static void orc_node(const OrcParams *p, int64_t index, int ntmpl, const int32_t *tx,
-                     const int32_t *ty, const int32_t *tz, const int64_t *nisb,
-                     const int32_t *lutx, const int32_t *luty, const int32_t *lutz,
-                     const double *sx, const double *sy, const double *sz,
-                     const double *sv, const double *ssec, const double *extgrid,
-                     const double *xdb, const double *ydb, const double *zdb,
-                     OrcCand *cand, double *work, double *est_out, double *var_out,
-                     int32_t *nbr_idx, int32_t *nbr_cnt)
+/*
+ * Body of the loop krige3d.py:302-403 for ONE location: (xloc, yloc, zloc) in super block
+ * (isx, isy, isz), external value extest (ktype 2/3).  koption != 0 (cross-validation /
+ * jackknife): samples at the location itself are not used (krige3d.py:359-363).
+ */
+static void orc_location(const OrcParams *p, double xloc, double yloc, double zloc, int isx,
+                         int isy, int isz, double extest, int koption, int ntmpl,
+                         const int32_t *tx, const int32_t *ty, const int32_t *tz,
+                         const int64_t *nisb, const double *sx, const double *sy,
+                         const double *sz, const double *sv, const double *ssec,
+                         const double *xdb, const double *ydb, const double *zdb,
+                         OrcCand *cand, double *work, double *est_out, double *var_out,
+                         int32_t *nbr_idx, int32_t *nbr_cnt)
 {
-    int64_t nxy = (int64_t)p->nx * p->ny;
-    int iz = (int)(index / nxy);
-    int iy = (int)((index - iz * nxy) / p->nx);
-    int ix = (int)(index - iz * nxy - (int64_t)iy * p->nx);
-    double xloc = p->xmn + ix * p->xsiz;
-    double yloc = p->ymn + iy * p->ysiz;
-    double zloc = p->zmn + iz * p->zsiz;
     double est = NAN, estv = NAN;
-    double extest = 0, resce = 0, skmean = p->skmean;
+    double resce = 0, skmean = p->skmean;
     int nused = 0;
     if (nbr_cnt)
         *nbr_cnt = 0;
 
     if (p->ktype == 2 || p->ktype == 3) { /* krige3d.py:334-344, repair D7 */
-        extest = extgrid[index];
         if (extest < p->tmin || extest >= p->tmax)
             goto done;
         resce = p->maxcov / (extest > 0.0001 ? extest : 0.0001);
     }
-    int nclose = orc_search(p, xloc, yloc, zloc, lutx[ix], luty[iy], lutz[iz], ntmpl,
+    int nclose = orc_search(p, xloc, yloc, zloc, isx, isy, isz, ntmpl,
                             tx, ty, tz, nisb, sx, sy, sz, cand);
-    int na = nclose < p->ndmax ? nclose : p->ndmax; /* krige3d.py:356-375 */
+    int na = 0; /* krige3d.py:356-375: the first ndmax accepted samples */
+    for (int i = 0; i < nclose && na < p->ndmax; i++) {
+        int64_t s = cand[i].i;
+        if (koption != 0 &&
+            fabs(sx[s] - xloc) + fabs(sy[s] - yloc) + fabs(sz[s] - zloc) < ORC_EPS)
+            continue;
+        cand[na++] = cand[i];
+    }
     nused = na;
     int mdt = orc_mdt(p);
     if (nbr_cnt)
@@ -479,6 +483,29 @@ done:
     *var_out = estv;
 }
 
+/* grid node `index` (x fastest, krige3d.py:303-309) */
+static void orc_node(const OrcParams *p, int64_t index, int ntmpl, const int32_t *tx,
+                     const int32_t *ty, const int32_t *tz, const int64_t *nisb,
+                     const int32_t *lutx, const int32_t *luty, const int32_t *lutz,
+                     const double *sx, const double *sy, const double *sz,
+                     const double *sv, const double *ssec, const double *extgrid,
+                     const double *xdb, const double *ydb, const double *zdb,
+                     OrcCand *cand, double *work, double *est_out, double *var_out,
+                     int32_t *nbr_idx, int32_t *nbr_cnt)
+{
+    int64_t nxy = (int64_t)p->nx * p->ny;
+    int iz = (int)(index / nxy);
+    int iy = (int)((index - iz * nxy) / p->nx);
+    int ix = (int)(index - iz * nxy - (int64_t)iy * p->nx);
+    double xloc = p->xmn + ix * p->xsiz;
+    double yloc = p->ymn + iy * p->ysiz;
+    double zloc = p->zmn + iz * p->zsiz;
+    double extest = (p->ktype == 2 || p->ktype == 3) ? extgrid[index] : 0.0;
+    orc_location(p, xloc, yloc, zloc, lutx[ix], luty[iy], lutz[iz], extest, 0, ntmpl, tx, ty,
+                 tz, nisb, sx, sy, sz, sv, ssec, xdb, ydb, zdb, cand, work, est_out, var_out,
+                 nbr_idx, nbr_cnt);
+}
+
 /*
  * Kriges nodes [node0, node1) of the grid (x fastest, krige3d.py:302-309) or, when
  * node_list != NULL, the nnodes flat indices it holds.  est/var/nbr are indexed by
@@ -513,6 +540,43 @@ int kt3d_oracle_run(const OrcParams *p, int64_t nd, const double *sx, const doub
                      nbr_idx ? nbr_idx + k * (int64_t)p->ndmax : NULL,
                      nbr_cnt ? nbr_cnt + k : NULL);
         }
+        free(cand);
+        free(work);
+    }
+    return 0;
+}
+
+/*
+ * Cross-validation / jackknife (krige3d.py:310-332, repair D11): kriges the npts listed
+ * locations; sb[3*k..] is the super block of location k (getindx, super_block.py:319-346),
+ * ext[k] its external-drift value (ktype 2/3).  Results indexed by k.
+ */
+int kt3d_oracle_run_points(const OrcParams *p, int64_t nd, const double *sx, const double *sy,
+                           const double *sz, const double *sv, const double *ssec,
+                           const int64_t *nisb, int ntmpl, const int32_t *tx,
+                           const int32_t *ty, const int32_t *tz, const double *xdb,
+                           const double *ydb, const double *zdb, int64_t npts,
+                           const double *px, const double *py, const double *pz,
+                           const double *ext, const int32_t *sb, int koption, double *est,
+                           double *var, int32_t *nbr_idx, int32_t *nbr_cnt, int nthreads)
+{
+    int neqmax = p->ndmax + ORC_MAXDRIFT + 2;
+#ifdef _OPENMP
+    if (nthreads > 0)
+        omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        OrcCand *cand = (OrcCand *)malloc(sizeof(OrcCand) * (size_t)(nd > 0 ? nd : 1));
+        double *work = (double *)malloc(sizeof(double) *
+                                        (size_t)(7 * neqmax + neqmax * neqmax));
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t k = 0; k < npts; k++)
+            orc_location(p, px[k], py[k], pz[k], sb[3 * k], sb[3 * k + 1], sb[3 * k + 2],
+                         ext ? ext[k] : 0.0, koption, ntmpl, tx, ty, tz, nisb, sx, sy, sz, sv,
+                         ssec, xdb, ydb, zdb, cand, work, est + k, var + k,
+                         nbr_idx ? nbr_idx + k * (int64_t)p->ndmax : NULL,
+                         nbr_cnt ? nbr_cnt + k : NULL);
         free(cand);
         free(work);
     }

@@ -250,7 +250,8 @@ def prepare(par, cols, prop_names):
               sv=np.ascontiguousarray(cols[prop_names[0]][sort_index]),
               ssec=np.ascontiguousarray(sec[sort_index]),
               nsup=(nxsup, nysup, nzsup), sizsup=(xsizsup, ysizsup, zsizsup),
-              mnsup=(xmnsup, ymnsup, zmnsup), block_of_sample=blk, cbb=P.cbb)
+              mnsup=(xmnsup, ymnsup, zmnsup), block_of_sample=blk, cbb=P.cbb,
+              node_edges=(ex, ey, ez))
     return st
 
 
@@ -281,6 +282,45 @@ def run(st, extgrid=None, node_range=None, node_list=None, threads=1, neighbours
         _p(st['lutx'], I32), _p(st['luty'], I32), _p(st['lutz'], I32),
         _p(extgrid, D), _p(st['xdb'], D), _p(st['ydb'], D), _p(st['zdb'], D),
         C.c_int64(n0), C.c_int64(n1), _p(node_list, I64), C.c_int64(count),
+        _p(est, D), _p(var, D), _p(nbr_idx, I32), _p(nbr_cnt, I32), C.c_int(threads))
+    return est, var, nbr_idx, nbr_cnt
+
+
+def super_block_of(st, px, py, pz):
+    """getindx (super_block.py:319-346): super block of arbitrary locations, with the
+    Numba-flavoured edges; clamped to the network (the reference does not clamp: parity is
+    defined for locations inside the grid extent)."""
+    out = []
+    for e, c, n in zip(st['node_edges'], (px, py, pz), st['nsup']):
+        out.append(np.clip(np.searchsorted(e, np.asarray(c, dtype=np.float64)) - 1, 0, n - 1))
+    return np.ascontiguousarray(np.stack(out, axis=1).astype(np.int32))
+
+
+def run_points(st, px, py, pz, ext=None, koption=1, threads=1, neighbours=True):
+    """Cross-validation (koption 1) / jackknife (koption 2) at the listed locations
+    (krige3d.py:310-332, 359-363).  Returns est, var, nbr_idx, nbr_cnt indexed by location."""
+    P = st['P']
+    L = lib()
+    D, I32, I64 = C.c_double, C.c_int32, C.c_int64
+    px, py, pz = (np.ascontiguousarray(a, dtype=np.float64) for a in (px, py, pz))
+    n = len(px)
+    sb = super_block_of(st, px, py, pz)
+    if P.ktype in (2, 3):
+        if ext is None:
+            raise ValueError("ikrige 2/3 needs the external value of every location")
+        ext = np.ascontiguousarray(ext, dtype=np.float64)
+    else:
+        ext = None
+    est = np.full(n, np.nan); var = np.full(n, np.nan)
+    nbr_idx = np.full((n, P.ndmax), -1, np.int32) if neighbours else None
+    nbr_cnt = np.zeros(n, np.int32)
+    L.kt3d_oracle_run_points.restype = C.c_int
+    L.kt3d_oracle_run_points(
+        C.byref(P), C.c_int64(len(st['sx'])), _p(st['sx'], D), _p(st['sy'], D),
+        _p(st['sz'], D), _p(st['sv'], D), _p(st['ssec'], D), _p(st['nisb'], I64),
+        C.c_int(st['ntmpl']), _p(st['tx'], I32), _p(st['ty'], I32), _p(st['tz'], I32),
+        _p(st['xdb'], D), _p(st['ydb'], D), _p(st['zdb'], D), C.c_int64(n),
+        _p(px, D), _p(py, D), _p(pz, D), _p(ext, D), _p(sb, I32), C.c_int(int(koption)),
         _p(est, D), _p(var, D), _p(nbr_idx, I32), _p(nbr_cnt, I32), C.c_int(threads))
     return est, var, nbr_idx, nbr_cnt
 

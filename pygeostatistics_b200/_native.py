@@ -51,6 +51,12 @@ class K3dOutputs(C.Structure):
                 ("nbr_cnt", C.c_void_p), ("status", C.c_void_p), ("ncand", C.c_void_p)]
 
 
+class K3dPoints(C.Structure):
+    _fields_ = [("npts", C.c_int64), ("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p),
+                ("ext", C.c_void_p), ("start", C.c_void_p),
+                ("exclude_coincident", C.c_int32), ("_pad", C.c_int32)]
+
+
 class K3dLaunchInfo(C.Structure):
     _fields_ = [("grid", C.c_int32), ("block", C.c_int32), ("smem_bytes", C.c_int32),
                 ("warps_per_cta", C.c_int32), ("stage_capacity", C.c_int32),
@@ -60,8 +66,9 @@ class K3dLaunchInfo(C.Structure):
 
 
 # every symbol include/k3d.h declares
-SYMBOLS = ("k3d_version", "k3d_last_error", "k3d_krige_slab", "k3d_build_template",
-           "k3d_krige_slab_host", "k3d_last_launch", "k3d_measure_fp64_peak")
+SYMBOLS = ("k3d_version", "k3d_last_error", "k3d_krige_slab", "k3d_krige_points",
+           "k3d_build_template", "k3d_krige_slab_host", "k3d_last_launch",
+           "k3d_measure_fp64_peak")
 
 _lib = None
 
@@ -80,6 +87,9 @@ def lib():
         L.k3d_krige_slab.restype = C.c_int
         L.k3d_krige_slab.argtypes = [C.POINTER(K3dParams), C.POINTER(K3dInputs), C.c_int32,
                                      C.c_int32, C.POINTER(K3dOutputs), C.c_void_p]
+        L.k3d_krige_points.restype = C.c_int
+        L.k3d_krige_points.argtypes = [C.POINTER(K3dParams), C.POINTER(K3dInputs),
+                                       C.POINTER(K3dPoints), C.POINTER(K3dOutputs), C.c_void_p]
         L.k3d_krige_slab_host.restype = C.c_int
         L.k3d_krige_slab_host.argtypes = [C.POINTER(K3dParams), C.POINTER(K3dInputs), C.c_int32,
                                           C.c_int32, C.POINTER(K3dOutputs)]

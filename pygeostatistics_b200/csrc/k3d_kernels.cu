@@ -485,12 +485,19 @@ __device__ __forceinline__ int octant_of_neg(double ndx, double ndy, double ndz)
 struct NodeCtx {
     double xloc, yloc, zloc;
     const double *qx, *qy, *qz; // candidate coordinate arrays addressed by slot
+    int excl;                   // 1: samples at the location itself are not used (krige3d.py:359-363)
 };
+
+// krige3d.py:359-362: |dx| + |dy| + |dz| < eps (arguments: location - sample)
+__device__ __forceinline__ bool coincident(double ndx, double ndy, double ndz)
+{
+    return __dadd_rn(__dadd_rn(fabs(ndx), fabs(ndy)), fabs(ndz)) < K3D_EPS;
+}
 
 // Sort the K collected candidates and keep what the reference would keep:
 // noct == 0 -> the ndmax nearest; noct > 0 -> per-octant nearest noct, at most 8*noct.
 __device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, double *keys,
-                                          int *slots, int K, int lane)
+                                          int *slots, int K, int lane, bool drop_self)
 {
     if (K > 1) {
         int n = 32;
@@ -514,8 +521,13 @@ __device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc,
         int slot = valid ? slots[j] : 0;
         double key = valid ? keys[j] : 0.0;
         int iq = 8;
-        if (valid)
-            iq = octant_of_neg(nc.xloc - nc.qx[slot], nc.yloc - nc.qy[slot], nc.zloc - nc.qz[slot]);
+        bool self = false;
+        if (valid) {
+            const double ndx = nc.xloc - nc.qx[slot], ndy = nc.yloc - nc.qy[slot],
+                         ndz = nc.zloc - nc.qz[slot];
+            iq = octant_of_neg(ndx, ndy, ndz);
+            self = drop_self && coincident(ndx, ndy, ndz);
+        }
         int rank = 0;
 #pragma unroll
         for (int o = 0; o < 8; o++) {
@@ -523,7 +535,9 @@ __device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc,
             if (iq == o) rank = cnt[o] + __popc(m & lt);
             cnt[o] += __popc(m);
         }
-        bool keep = valid && rank < P.noct;
+        // a sample at the location itself takes its place in the octant (the search does not
+        // know about it, super_block.py:185-224) and is dropped afterwards (krige3d.py:359)
+        bool keep = valid && rank < P.noct && !self;
         unsigned km = __ballot_sync(FULL, keep);
         __syncwarp();
         if (keep) {
@@ -540,9 +554,9 @@ __device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc,
 // out-of-line copy for the rare mid-scan overflow (hot call sites inline prune_list so that
 // the list stays addressed as shared memory and the parameters as constants)
 __device__ __noinline__ int prune_list_cold(const K3dParams &P, const NodeCtx &nc, double *keys,
-                                            int *slots, int K, int lane)
+                                            int *slots, int K, int lane, bool drop_self)
 {
-    return prune_list(P, nc, keys, slots, K, lane);
+    return prune_list(P, nc, keys, slots, K, lane, drop_self);
 }
 
 // Selection for short lists (K <= 64, the usual case once the bounds of the previous node
@@ -552,14 +566,16 @@ __device__ __noinline__ int prune_list_cold(const K3dParams &P, const NodeCtx &n
 // at the front of the list; which ones are kept is exactly what the sort + octant pass keeps.
 __device__ __forceinline__ int select_small(const K3dParams &P, double *keys, int *slots,
                                             const unsigned char *octs, int K, int lane)
-{
+{   // octs[]: octant in bits 0-2; bit 7 = sample at the location itself (octant search of a
+    // cross-validation: it counts in its octant and is dropped afterwards)
     const unsigned lt = (1u << lane) - 1u;
     bool v0 = lane < K, v1 = lane + 32 < K;
     const double k0 = v0 ? keys[lane] : 0.0, k1 = v1 ? keys[lane + 32] : 0.0;
     const unsigned hi0 = (unsigned)__double2hiint(k0), lo0 = (unsigned)__double2loint(k0);
     const unsigned hi1 = (unsigned)__double2hiint(k1), lo1 = (unsigned)__double2loint(k1);
     const int s0 = v0 ? slots[lane] : 0, s1 = v1 ? slots[lane + 32] : 0;
-    const int o0 = v0 ? octs[lane] : 8, o1 = v1 ? octs[lane + 32] : 8;
+    const int f0 = v0 ? octs[lane] : 8, f1 = v1 ? octs[lane + 32] : 8;
+    const int o0 = f0 & 15, o1 = f1 & 15;
     // removes the lexicographically largest element among those flagged a0 / a1
     auto remove_max = [&](bool a0, bool a1) {
         const bool use1 = a1 && (!a0 || hi1 > hi0 || (hi1 == hi0 && (lo1 > lo0 || (lo1 == lo0 && s1 > s0))));
@@ -586,6 +602,8 @@ __device__ __forceinline__ int select_small(const K3dParams &P, double *keys, in
             int c = __popc(__ballot_sync(FULL, v0 && o0 == o)) + __popc(__ballot_sync(FULL, v1 && o1 == o));
             for (; c > P.noct; c--) remove_max(v0 && o0 == o, v1 && o1 == o);
         }
+        v0 = v0 && !(f0 & 0x80);
+        v1 = v1 && !(f1 & 0x80);
     }
     int total = __popc(__ballot_sync(FULL, v0)) + __popc(__ballot_sync(FULL, v1));
     for (; total > P.ndmax; total--) remove_max(v0, v1);
@@ -623,18 +641,24 @@ __device__ __forceinline__ int scan_candidates(const K3dParams &P, const int kca
             // reference: `if hsqd > radsqd: continue`; tau[] <= radsqd are exact upper
             // bounds of what can still be selected in the sample's octant
             oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
-            in = !(h > tau[oq]);
+            in = !(h > tau[oq & 7]);
+            if (nc.excl && coincident(dx, dy, dz)) { // krige3d.py:359-363
+                if (P.noct > 0) oq |= 0x80; // still takes its place in the octant
+                else in = false;
+            }
         }
         unsigned m = __ballot_sync(FULL, in);
         if (m == 0u)
             continue;
         if (K + 32 > kcap) { // rare: thin the list (sorted afterwards); re-derive octants
             __syncwarp();
-            K = prune_list_cold(P, nc, keys, slots, K, lane);
+            K = prune_list_cold(P, nc, keys, slots, K, lane, false); // keeps a sample at the location
             for (int t = lane; t < K; t += 32) {
                 const int sl = slots[t];
-                octs[t] = (unsigned char)(P.noct > 0 ? octant_of_neg(nc.xloc - nc.qx[sl], nc.yloc - nc.qy[sl],
-                                                                      nc.zloc - nc.qz[sl]) : 0);
+                const double ndx = nc.xloc - nc.qx[sl], ndy = nc.yloc - nc.qy[sl], ndz = nc.zloc - nc.qz[sl];
+                int oq2 = P.noct > 0 ? octant_of_neg(ndx, ndy, ndz) : 0;
+                if (P.noct > 0 && nc.excl && coincident(ndx, ndy, ndz)) oq2 |= 0x80;
+                octs[t] = (unsigned char)oq2;
             }
             __syncwarp();
         }
@@ -664,12 +688,21 @@ struct Tile {
     int sbx, sby, sbz;  // super block
     int x0, y0, z0;     // first node (z clipped to the slab)
     int tnx, tny, tnz;  // nodes per axis
-    int tnodes;
+    int tnodes;         // grid nodes of the tile, or listed locations of the super block
     int zsb0;           // first node plane of the super block (unclipped)
+    int first;          // locations mode: index of the tile's first location
+};
+
+// Estimation at listed locations instead of grid nodes (cross-validation / jackknife,
+// krige3d.py:310-332): device copy of K3dPoints; x == NULL means grid mode.
+struct PtSet {
+    const double *x, *y, *z, *ext;
+    const int32_t *start;
+    int exclude;
 };
 
 __device__ __forceinline__ Tile tile_of_block(const K3dParams &P, const K3dInputs &in, int iz0,
-                                              int iz1)
+                                              int iz1, const PtSet &pts)
 {
     Tile T;
     int tile = blockIdx.x;
@@ -680,6 +713,14 @@ __device__ __forceinline__ Tile tile_of_block(const K3dParams &P, const K3dInput
     T.x0 = in.nodex0[T.sbx];
     T.y0 = in.nodey0[T.sby];
     T.zsb0 = in.nodez0[T.sbz];
+    T.first = 0;
+    if (pts.x) { // the tile's "nodes" are the locations listed for this super block
+        T.first = pts.start[blockIdx.x];
+        T.tnodes = pts.start[blockIdx.x + 1] - T.first;
+        T.z0 = T.zsb0;
+        T.tnx = T.tny = T.tnz = 1;
+        return T;
+    }
     int z1 = in.nodez0[T.sbz + 1];
     T.z0 = T.zsb0 > iz0 ? T.zsb0 : iz0;
     z1 = z1 < iz1 ? z1 : iz1;
@@ -688,6 +729,32 @@ __device__ __forceinline__ Tile tile_of_block(const K3dParams &P, const K3dInput
     T.tnz = z1 - T.z0;
     T.tnodes = (T.tnx > 0 && T.tny > 0 && T.tnz > 0) ? T.tnx * T.tny * T.tnz : 0;
     return T;
+}
+
+// location of the tile's t-th node and its index in the output arrays
+struct NodeLoc {
+    double x, y, z;
+    size_t o;
+};
+__device__ __forceinline__ void snake_node(const Tile &T, int t, int &lx, int &ly, int &lz);
+__device__ __forceinline__ NodeLoc node_of_tile(const K3dParams &P, const Tile &T, const PtSet &pts,
+                                                int t, size_t slab_off)
+{
+    NodeLoc L;
+    if (pts.x) {
+        L.o = (size_t)(T.first + t);
+        L.x = pts.x[L.o]; L.y = pts.y[L.o]; L.z = pts.z[L.o];
+        return L;
+    }
+    int lx, ly, lz;
+    snake_node(T, t, lx, ly, lz);
+    const int ix = T.x0 + lx, iy = T.y0 + ly, iz = T.z0 + lz;
+    L.o = (((size_t)iz * P.ny + iy) * P.nx + ix) - slab_off;
+    // krige3d.py:307-309: xmn + ix*xsiz, multiply then add, unfused
+    L.x = __dadd_rn(P.xmn, __dmul_rn((double)ix, P.xsiz));
+    L.y = __dadd_rn(P.ymn, __dmul_rn((double)iy, P.ysiz));
+    L.z = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
+    return L;
 }
 
 // node t of the tile's boustrophedon path: consecutive t are grid neighbours
@@ -710,7 +777,7 @@ __global__ void __launch_bounds__(256, 4)
 k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const int iz0,
                   const int iz1, int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
                   int32_t *__restrict__ ncand_out, const int ordered,
-                  const __grid_constant__ SCfg cfg)
+                  const __grid_constant__ SCfg cfg, const __grid_constant__ PtSet pts)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -731,7 +798,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
 
     __shared__ int s_total, s_warpsum[32];
 
-    const Tile T = tile_of_block(P, in, iz0, iz1);
+    const Tile T = tile_of_block(P, in, iz0, iz1, pts);
     if (T.tnodes <= 0)
         return;
     const int sbx = T.sbx, sby = T.sby, sbz = T.sbz;
@@ -803,6 +870,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     nc.qx = staged ? stx : in.sx;
     nc.qy = staged ? sty : in.sy;
     nc.qz = staged ? stz : in.sz;
+    nc.excl = pts.x ? pts.exclude : 0;
 
     // ---- each warp walks a contiguous piece of a boustrophedon path through the tile:
     //      consecutive nodes are grid neighbours, so their neighbourhoods overlap ---------
@@ -816,24 +884,45 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     // walk (triangle inequality), so the per-node scans only visit the others.
     int nsubw = -1; // length of sub[], or -1: scan every staged candidate
     if (staged && t_begin < t_end) {
-        int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
-        for (int t = t_begin + lane; t < t_end; t += 32) {
-            int lx, ly, lz;
-            snake_node(T, t, lx, ly, lz);
-            lo[0] = min(lo[0], lx); hi[0] = max(hi[0], lx);
-            lo[1] = min(lo[1], ly); hi[1] = max(hi[1], ly);
-            lo[2] = min(lo[2], lz); hi[2] = max(hi[2], lz);
-        }
+        double bcx, bcy, bcz, ex, ey, ez; // centre and half extents of the walk's bounding box
+        if (pts.x) {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int t = t_begin + lane; t < t_end; t += 32) {
+                const size_t q = (size_t)(T.first + t);
+                lo[0] = fmin(lo[0], pts.x[q]); hi[0] = fmax(hi[0], pts.x[q]);
+                lo[1] = fmin(lo[1], pts.y[q]); hi[1] = fmax(hi[1], pts.y[q]);
+                lo[2] = fmin(lo[2], pts.z[q]); hi[2] = fmax(hi[2], pts.z[q]);
+            }
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            lo[k] = __reduce_min_sync(FULL, lo[k]);
-            hi[k] = __reduce_max_sync(FULL, hi[k]);
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    lo[k] = fmin(lo[k], __shfl_xor_sync(FULL, lo[k], d));
+                    hi[k] = fmax(hi[k], __shfl_xor_sync(FULL, hi[k], d));
+                }
+            bcx = 0.5 * (lo[0] + hi[0]); bcy = 0.5 * (lo[1] + hi[1]); bcz = 0.5 * (lo[2] + hi[2]);
+            // (the 1e-9 margin on `reach` below also covers the rounding of these halves)
+            ex = 0.5 * (hi[0] - lo[0]); ey = 0.5 * (hi[1] - lo[1]); ez = 0.5 * (hi[2] - lo[2]);
+        } else {
+            int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
+            for (int t = t_begin + lane; t < t_end; t += 32) {
+                int lx, ly, lz;
+                snake_node(T, t, lx, ly, lz);
+                lo[0] = min(lo[0], lx); hi[0] = max(hi[0], lx);
+                lo[1] = min(lo[1], ly); hi[1] = max(hi[1], ly);
+                lo[2] = min(lo[2], lz); hi[2] = max(hi[2], lz);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                lo[k] = __reduce_min_sync(FULL, lo[k]);
+                hi[k] = __reduce_max_sync(FULL, hi[k]);
+            }
+            bcx = P.xmn + (T.x0 + 0.5 * (lo[0] + hi[0])) * P.xsiz;
+            bcy = P.ymn + (T.y0 + 0.5 * (lo[1] + hi[1])) * P.ysiz;
+            bcz = P.zmn + (T.z0 + 0.5 * (lo[2] + hi[2])) * P.zsiz;
+            ex = 0.5 * (hi[0] - lo[0]) * fabs(P.xsiz); ey = 0.5 * (hi[1] - lo[1]) * fabs(P.ysiz);
+            ez = 0.5 * (hi[2] - lo[2]) * fabs(P.zsiz);
         }
-        const double bcx = P.xmn + (T.x0 + 0.5 * (lo[0] + hi[0])) * P.xsiz,
-                     bcy = P.ymn + (T.y0 + 0.5 * (lo[1] + hi[1])) * P.ysiz,
-                     bcz = P.zmn + (T.z0 + 0.5 * (lo[2] + hi[2])) * P.zsiz;
-        const double ex = 0.5 * (hi[0] - lo[0]) * fabs(P.xsiz), ey = 0.5 * (hi[1] - lo[1]) * fabs(P.ysiz),
-                     ez = 0.5 * (hi[2] - lo[2]) * fabs(P.zsiz);
         const double *rs = P.rotmat + 9 * P.nst;
         double rho2 = 0.0; // corners come in +- pairs: four sign patterns suffice
         rho2 = fmax(rho2, sqdist_exact(ex, ey, ez, rs));
@@ -858,14 +947,9 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     }
 
     for (int t = t_begin; t < t_end; t++) {
-        int lx, ly, lz;
-        snake_node(T, t, lx, ly, lz);
-        const int ix = T.x0 + lx, iy = T.y0 + ly, iz = T.z0 + lz;
-        const size_t o = (((size_t)iz * P.ny + iy) * P.nx + ix) - slab_off;
-        // krige3d.py:307-309: xmn + ix*xsiz, multiply then add, unfused
-        nc.xloc = __dadd_rn(P.xmn, __dmul_rn((double)ix, P.xsiz));
-        nc.yloc = __dadd_rn(P.ymn, __dmul_rn((double)iy, P.ysiz));
-        nc.zloc = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
+        const NodeLoc L = node_of_tile(P, T, pts, t, slab_off);
+        const size_t o = L.o;
+        nc.xloc = L.x; nc.yloc = L.y; nc.zloc = L.z;
         int tested = 0;
 
         // ---- 0. exact upper bounds from the previous node's neighbours ----------------
@@ -890,6 +974,8 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                                dz = __dsub_rn(nc.zloc, nc.qz[s]);
                         double h = sqdist_exact(dx, dy, dz, rs);
                         inr = !(h > P.radsqd);
+                        // without octants a sample at the location itself is never a candidate
+                        if (nc.excl && P.noct <= 0 && coincident(dx, dy, dz)) inr = false;
                         oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
                         hi = (unsigned)__double2hiint(h);
                         lo = (unsigned)__double2loint(h);
@@ -957,9 +1043,9 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         } else if (staged) {
             NodeCtx ns = nc;
             ns.qx = stx; ns.qy = sty; ns.qz = stz;
-            K = prune_list(P, ns, keys, slots, K, lane);
+            K = prune_list(P, ns, keys, slots, K, lane, ns.excl != 0);
         } else {
-            K = prune_list_cold(P, nc, keys, slots, K, lane);
+            K = prune_list_cold(P, nc, keys, slots, K, lane, nc.excl != 0);
         }
         nhint = K < K3D_NHINT ? K : K3D_NHINT; // this node's neighbours seed the next bounds
         if (lane < nhint) hint[lane] = slots[lane];
@@ -986,7 +1072,7 @@ __global__ void __launch_bounds__(AMAX == 5 ? 256 : 640, AMAX == 5 ? K3D_SMALL_C
 k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
                  const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
                  const int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
-                 const __grid_constant__ BCfg cfg)
+                 const __grid_constant__ BCfg cfg, const __grid_constant__ PtSet pts)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1016,7 +1102,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     unsigned short *s_rtab = (unsigned short *)(smem + b_off_rtab(cfg)); // (warp << 8) | round
     __shared__ double s_jloc[20][3]; // per warp: node location
 
-    const Tile T = tile_of_block(P, in, iz0, iz1);
+    const Tile T = tile_of_block(P, in, iz0, iz1, pts);
     if (T.tnodes <= 0)
         return;
     // structure-space origin of the tile: first node of the super block (slab independent)
@@ -1057,14 +1143,9 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     for (int tt = 0; tt < per; tt++) {
         const int t = t_begin + tt;
         const bool active = t < t_end;
-        int lx = 0, ly = 0, lz = 0;
-        if (active) snake_node(T, t, lx, ly, lz);
-        const int ix = T.x0 + lx, iy = T.y0 + ly, iz = T.z0 + lz;
-        const size_t o = (((size_t)iz * P.ny + iy) * P.nx + ix) - slab_off;
-        // krige3d.py:307-309: xmn + ix*xsiz, multiply then add, unfused
-        const double xloc = __dadd_rn(P.xmn, __dmul_rn((double)ix, P.xsiz));
-        const double yloc = __dadd_rn(P.ymn, __dmul_rn((double)iy, P.ysiz));
-        const double zloc = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
+        const NodeLoc L = node_of_tile(P, T, pts, active ? t : 0, slab_off);
+        const size_t o = L.o;
+        const double xloc = L.x, yloc = L.y, zloc = L.z;
         double est = NaN, var = NaN;
         int status = K3D_ST_OK;
         int na = 0;
@@ -1072,7 +1153,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
 
         bool live = active;
         if (has_ext && active) { // krige3d.py:334-344
-            extest = in.extgrid[o];
+            extest = pts.x ? pts.ext[o] : in.extgrid[o];
             if (extest < P.tmin || extest >= P.tmax) {
                 status = K3D_ST_EXT_TRIMMED;
                 live = false;
@@ -1624,12 +1705,12 @@ int scratch_pool(int dev, cudaMemPool_t *pool)
 template <int AMAX, bool BLOCK>
 int launch_solve2(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
                   int iz0, int iz1, const int32_t *nbr, int32_t *cnt, const BCfg &c,
-                  long long ntiles, cudaStream_t st)
+                  long long ntiles, cudaStream_t st, const PtSet &ps)
 {
     CUDA_TRY(cudaFuncSetAttribute(k3d_solve_kernel<AMAX, BLOCK>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
     k3d_solve_kernel<AMAX, BLOCK><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(
-        *p, *q, *in, *out, iz0, iz1, nbr, cnt, c);
+        *p, *q, *in, *out, iz0, iz1, nbr, cnt, c, ps);
     CUDA_TRY(cudaGetLastError());
     return K3D_OK;
 }
@@ -1637,10 +1718,10 @@ int launch_solve2(const K3dParams *p, const KPrep *q, const K3dInputs *in, const
 template <int AMAX>
 int launch_solve(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
                  int iz0, int iz1, const int32_t *nbr, int32_t *cnt, const BCfg &c,
-                 long long ntiles, cudaStream_t st)
+                 long long ntiles, cudaStream_t st, const PtSet &ps)
 {
-    return p->ndb > 1 ? launch_solve2<AMAX, true>(p, q, in, out, iz0, iz1, nbr, cnt, c, ntiles, st)
-                      : launch_solve2<AMAX, false>(p, q, in, out, iz0, iz1, nbr, cnt, c, ntiles, st);
+    return p->ndb > 1 ? launch_solve2<AMAX, true>(p, q, in, out, iz0, iz1, nbr, cnt, c, ntiles, st, ps)
+                      : launch_solve2<AMAX, false>(p, q, in, out, iz0, iz1, nbr, cnt, c, ntiles, st, ps);
 }
 
 } // namespace
@@ -1668,7 +1749,7 @@ int k3d_last_launch(K3dLaunchInfo *info)
 }
 
 static int validate(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
-                    const K3dOutputs *out)
+                    const K3dOutputs *out, bool points = false)
 {
     if (!p || !in || !out) return fail(K3D_EINVAL, "NULL argument");
     if (p->nx < 1 || p->ny < 1 || p->nz < 1) return fail(K3D_EINVAL, "empty grid");
@@ -1684,7 +1765,7 @@ static int validate(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_
     if (!in->sx || !in->sy || !in->sz || !in->sv || !in->sbstart || !in->runs ||
         !in->nodex0 || !in->nodey0 || !in->nodez0 || !in->dbxyz)
         return fail(K3D_EINVAL, "NULL input array");
-    if ((p->ktype == 2 || p->ktype == 3) && (!in->ssec || !in->extgrid))
+    if ((p->ktype == 2 || p->ktype == 3) && (!in->ssec || (!in->extgrid && !points)))
         return fail(K3D_EINVAL, "ikrige 2/3 needs ssec and extgrid");
     if (!out->est || !out->var) return fail(K3D_EINVAL, "NULL output array");
     if ((int64_t)p->nxsup * p->nysup * p->nzsup > 0x7fffffff || in->nd > 0x7fffffff)
@@ -1692,19 +1773,30 @@ static int validate(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_
     return K3D_OK;
 }
 
-int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
-                   const K3dOutputs *out, void *stream)
+// Both entry points: grid nodes of planes [iz0, iz1), or (pts != NULL) the listed locations
+static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
+                     const K3dOutputs *out, const K3dPoints *pts, void *stream)
 {
-    int rc = validate(p, in, iz0, iz1, out);
+    int rc = validate(p, in, iz0, iz1, out, pts != nullptr);
     if (rc) return rc;
     if (iz0 == iz1) return K3D_OK;
+    PtSet ps = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    if (pts) {
+        if (pts->npts < 0 || pts->npts > 0x7fffffff) return fail(K3D_EINVAL, "bad number of locations");
+        if (pts->npts == 0) return K3D_OK;
+        if (!pts->x || !pts->y || !pts->z || !pts->start) return fail(K3D_EINVAL, "NULL location array");
+        if ((p->ktype == 2 || p->ktype == 3) && !pts->ext)
+            return fail(K3D_EINVAL, "ikrige 2/3 needs the external value of every location");
+        ps.x = pts->x; ps.y = pts->y; ps.z = pts->z; ps.ext = pts->ext; ps.start = pts->start;
+        ps.exclude = pts->exclude_coincident ? 1 : 0;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, smem_max = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const double nsb = (double)p->nxsup * p->nysup * p->nzsup;
     const double mean_cand = in->ntmpl > 0 ? (double)in->nd / nsb * in->ntmpl : 512.0;
-    const double tile_nodes = (double)p->nx * p->ny * p->nz / nsb;
+    const double tile_nodes = pts ? (double)pts->npts / nsb : (double)p->nx * p->ny * p->nz / nsb;
     SCfg sc;
     BCfg bc;
     if (make_scfg(p, mean_cand, tile_nodes, smem_max, &sc) != K3D_OK ||
@@ -1721,7 +1813,9 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
     // neighbour lists travel from the search kernel to the solve kernel through global
     // memory: the caller's arrays when given, else stream-ordered scratch, at most ~4 GB at
     // a time (the slab is then processed in equal runs of z-planes)
-    const size_t plane = (size_t)p->nx * p->ny;
+    // (locations mode: one "plane" holding every location, one run)
+    const size_t plane = pts ? (size_t)pts->npts : (size_t)p->nx * p->ny;
+    if (pts) { iz0 = 0; iz1 = 1; }
     const size_t per_plane = plane * ((out->nbr_idx ? 0 : (size_t)p->ndmax * 4) + (out->nbr_cnt ? 0 : 4));
     int zstep = iz1 - iz0;
     if (per_plane > 0) {
@@ -1730,7 +1824,7 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
             if (atoll(e) > 0) cap = (size_t)atoll(e) << 20;
         size_t fit = cap / per_plane;
         if (fit < 1) fit = 1;
-        if ((size_t)zstep > fit) {
+        if (!pts && (size_t)zstep > fit) {
             const int nruns = (int)(((size_t)zstep + fit - 1) / fit);
             zstep = (zstep + nruns - 1) / nruns;
         }
@@ -1765,14 +1859,14 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
         int32_t *cnt = co.nbr_cnt ? co.nbr_cnt : scnt;
         cudaEventRecord(g_ev[0], st);
         k3d_search_kernel<<<(unsigned)ntiles, sc.warps * 32, sc.smem_bytes, st>>>(
-            *p, ci, za, zb, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc);
+            *p, ci, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc, ps);
         if (cudaGetLastError() != cudaSuccess) { rc = fail(K3D_ECUDA, "search kernel launch failed"); break; }
         cudaEventRecord(g_ev[1], st);
         switch (amax_for(bc.rtot)) {
-        case 5: rc = launch_solve<5>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
-        case 9: rc = launch_solve<9>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
-        case 11: rc = launch_solve<11>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
-        default: rc = launch_solve<0>(p, &q, &ci, &co, za, zb, nbr, cnt, bc, ntiles, st); break;
+        case 5: rc = launch_solve<5>(p, &q, &ci, &co, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, bc, ntiles, st, ps); break;
+        case 9: rc = launch_solve<9>(p, &q, &ci, &co, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, bc, ntiles, st, ps); break;
+        case 11: rc = launch_solve<11>(p, &q, &ci, &co, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, bc, ntiles, st, ps); break;
+        default: rc = launch_solve<0>(p, &q, &ci, &co, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, bc, ntiles, st, ps); break;
         }
         cudaEventRecord(g_ev[2], st);
         g_ev_pending = true;
@@ -1790,6 +1884,19 @@ int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t
     g_launch.search_block = sc.warps * 32;
     g_launch.search_smem_bytes = sc.smem_bytes;
     return K3D_OK;
+}
+
+int k3d_krige_slab(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
+                   const K3dOutputs *out, void *stream)
+{
+    return krige_run(p, in, iz0, iz1, out, nullptr, stream);
+}
+
+int k3d_krige_points(const K3dParams *p, const K3dInputs *in, const K3dPoints *pts,
+                     const K3dOutputs *out, void *stream)
+{
+    if (!pts) return fail(K3D_EINVAL, "NULL argument");
+    return krige_run(p, in, 0, p ? p->nz : 0, out, pts, stream);
 }
 
 int k3d_build_template(int32_t nxsup, int32_t nysup, int32_t nzsup, double xsizsup,

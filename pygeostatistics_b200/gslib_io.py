@@ -111,3 +111,21 @@ def write_gslib_grid(path, estimate, variance, title="kt3d estimates", unest=Non
     with open(path, "w") as fout:
         fout.write("%s\n2\nEstimate\nEstimationVariance\n" % title)
         np.savetxt(fout, np.column_stack([est, var]), fmt="%.17g", delimiter="\t")
+
+
+def write_gslib_validation(path, xyz, true, estimate, variance, title="kt3d cross validation",
+                           unest=None):
+    """Cross-validation / jackknife output, one record per location: X, Y, Z, True,
+    Estimate, EstimationVariance, Error = estimate - true (GSLIB kt3d's layout for
+    `option` 1 and 2; gslib_help/kt3d_help.md:20-27 names the option, the reference writes
+    nothing)."""
+    xyz = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
+    cols = [xyz[:, 0], xyz[:, 1], xyz[:, 2]] + [np.asarray(a, dtype=np.float64)
+                                                for a in (true, estimate, variance)]
+    cols.append(cols[4] - cols[3])
+    table = np.column_stack(cols)
+    if unest is not None:
+        table = np.where(np.isnan(table), unest, table)
+    with open(path, "w") as fout:
+        fout.write("%s\n7\nX\nY\nZ\nTrue\nEstimate\nEstimationVariance\nError: est-true\n" % title)
+        np.savetxt(fout, table, fmt="%.17g", delimiter="\t")

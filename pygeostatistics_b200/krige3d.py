@@ -25,7 +25,8 @@ import numpy as np
 import torch
 
 from . import _native
-from .gslib_io import SpatialData, read_params, read_grid_column, write_gslib_grid
+from .gslib_io import (SpatialData, read_params, read_grid_column, write_gslib_grid,
+                       write_gslib_validation)
 from .super_block import SuperBlockSearcher
 
 EPS = np.finfo(float).eps
@@ -102,16 +103,20 @@ class _MemoryData(object):
 class Krige3d(object):
     """Performing 3d Kriging with super block search (GPU)."""
 
-    def __init__(self, param_file, data=None, secondary=None):
+    def __init__(self, param_file, data=None, secondary=None, jackknife=None):
         """`param_file`: path of a JSON .par file (as in the reference), or the same
         mapping already parsed.  `data` (optional): ordered mapping column name -> 1-D
         array used instead of reading `datafl`; `secondary` (optional): the external-drift
-        value of every grid node (x fastest) used instead of reading `secfl`."""
+        value of every grid node (x fastest) used instead of reading `secfl`; `jackknife`
+        (optional, `option` 2): the same kind of mapping used instead of reading `jackfl`."""
         self.param_file = param_file
         self._read_params()
         self._check_params()
         self.data = SpatialData(self.datafl) if data is None else _MemoryData(data)
         self._secondary = secondary
+        self._jackknife = jackknife
+        self.locations = None      # option 1/2: (n, 3) estimated locations, file order
+        self.true_values = None    # option 1/2: the value observed at each location
         self.property_name = self.data.property_name
         self.vr = self.data.vr
         self.rotmat = None
@@ -191,9 +196,8 @@ class Krige3d(object):
             raise ValueError("nst > {} is not supported".format(_native.MAXNST))
         if not 1 <= self.ndmax <= _native.MAXNDMAX:
             raise ValueError("ndmax must be in 1..{}".format(_native.MAXNDMAX))
-        if self.koption != 0:
-            raise NotImplementedError("cross-validation / jackknife (option 1, 2) is not "
-                                      "implemented (it crashes in the reference as well)")
+        if self.koption not in (0, 1, 2):
+            raise ValueError("option must be 0 (grid), 1 (cross-validation) or 2 (jackknife)")
 
     def read_data(self):
         """(Re)load `datafl`.  The reference does this in the constructor."""
@@ -219,6 +223,10 @@ class Krige3d(object):
         self.sanis2 = self.radius_vert / self.radius_hmax
         self.anis1 = np.array(self.aa_hmin) / np.maximum(self.aa_hmax, EPS)
         self.anis2 = np.array(self.aa_vert) / np.maximum(self.aa_hmax, EPS)
+        if self.koption == 1:  # cross-validation: the data file is the jackknife file
+            self.jackfl = self.datafl  # krige3d.py:200-208
+            self.ixlj, self.iylj, self.izlj = self.ixl, self.iyl, self.izl
+            self.ivrlj, self.iextvj = self.ivrl, self.iextv
 
     def _set_rotation(self):
         """rotmat[(nst+1),3,3]; the last matrix is the search ellipsoid (krige3d.py:211-253).
@@ -397,7 +405,7 @@ class Krige3d(object):
         d['extgrid'] = None if ext_slab is None else ext_slab.to(dev, non_blocking=True)
         return d
 
-    def _launch(self, P, d, iz0, iz1, out):
+    def _inputs_struct(self, d):
         ptr = lambda t: C.c_void_p(None if t is None else t.data_ptr())
         I = _native.K3dInputs()
         I.nd = int(d['sx'].numel())
@@ -407,11 +415,19 @@ class Krige3d(object):
         I.ntmpl = int(self.searcher.nsbtosr)
         I.nodex0, I.nodey0, I.nodez0 = ptr(d['nodex0']), ptr(d['nodey0']), ptr(d['nodez0'])
         I.dbxyz, I.extgrid = ptr(d['dbxyz']), ptr(d['extgrid'])
+        return I
+
+    def _outputs_struct(self, out):
+        ptr = lambda t: C.c_void_p(None if t is None else t.data_ptr())
         O = _native.K3dOutputs()
         O.est, O.var = ptr(out['est']), ptr(out['var'])
         O.nbr_idx, O.nbr_cnt, O.status = ptr(out.get('nbr_idx')), ptr(out.get('nbr_cnt')), \
             ptr(out.get('status'))
         O.ncand = ptr(out.get('ncand'))
+        return O
+
+    def _launch(self, P, d, iz0, iz1, out):
+        I, O = self._inputs_struct(d), self._outputs_struct(out)
         stream = torch.cuda.current_stream(self._device()).cuda_stream
         _native.check(_native.lib().k3d_krige_slab(C.byref(P), C.byref(I), iz0, iz1,
                                                   C.byref(O), C.c_void_p(stream)))
@@ -485,6 +501,8 @@ class Krige3d(object):
         z-slabs, one per rank; every rank ends up with the full arrays."""
         import torch.distributed as dist
         self.prepare()
+        if self.koption != 0:
+            return self._kt3d_locations(neighbours)
         P = self._params_struct()
         world, rank = 1, 0
         if dist.is_available() and dist.is_initialized():
@@ -551,13 +569,99 @@ class Krige3d(object):
         if self.verbose:
             print("Kriging Finished.")
 
+    # ------------------------------------------------------------------ option 1 / 2
+    def _read_locations(self):
+        """Where to estimate for `option` 1 (cross-validation: the data themselves) and 2
+        (jackknife: the records of `jackfl`), krige3d.py:200-208, 310-332.  The reference
+        never reads the file (its loop indexes an empty list); like `datafl`, `jackfl` is a
+        Geo-EAS file whose columns are taken by NAME: x, y[, z], then the variable and, for
+        ikrige 2/3, the external-drift variable.  Returns x, y, z, true, ext (file order)."""
+        if self.koption == 1:
+            src, prop = self.data.vr, self.data.property_name
+        else:
+            jk = SpatialData(self.jackfl) if self._jackknife is None else _MemoryData(self._jackknife)
+            src, prop = jk.vr, jk.property_name
+        col = lambda nm: np.ascontiguousarray(src[nm], dtype=np.float64)
+        x, y, z = col('x'), col('y'), col('z')
+        true = col(prop[0]) if len(prop) > 0 else np.full(x.shape, np.nan)
+        true = np.where((true < self.tmin) | (true >= self.tmax), np.nan, true)  # krige3d.py:331
+        ext = None
+        if self.ktype in (2, 3):
+            if len(prop) < 2:
+                raise ValueError("ikrige 2/3 needs the external variable at every location")
+            ext = col(prop[1])
+        return x, y, z, true, ext
+
+    def _kt3d_locations(self, neighbours=False):
+        """Cross-validation / jackknife: the same two kernels, with the listed locations
+        grouped by super block in place of the grid nodes (k3d_krige_points).  Every rank of
+        a process group computes all locations (these runs are small)."""
+        t0 = time.time()
+        x, y, z, true, ext = self._read_locations()
+        n = x.shape[0]
+        s = self.searcher
+        blk = s.block_of_locations(x, y, z)
+        order = np.argsort(blk, kind='stable')
+        nsup = s.nxsup * s.nysup * s.nzsup
+        start = np.concatenate([[0], np.cumsum(np.bincount(blk, minlength=nsup))]).astype(np.int32)
+        dev = self._device()
+        up = lambda a: None if a is None else torch.from_numpy(
+            np.ascontiguousarray(a)).pin_memory().to(dev, non_blocking=True)
+        pt = dict(x=up(x[order]), y=up(y[order]), z=up(z[order]),
+                  ext=None if ext is None else up(ext[order]), start=up(start))
+        d = self._upload(self._host_inputs(), None)
+        out = self._alloc_outputs(n, neighbours)
+        if n > 0:
+            self._launch_points(self._params_struct(), d, pt, n, out)
+        res = {}
+        for k, v in out.items():
+            view, arr = _pinned_array(v.numel(), v.dtype)
+            view.copy_(v, non_blocking=True)
+            res[k] = arr
+        torch.cuda.synchronize(dev)
+        inv = np.empty(n, dtype=np.int64)
+        inv[order] = np.arange(n)
+        self.locations = np.stack([x, y, z], axis=1)
+        self.true_values = true
+        self.estimation = res['est'][inv]
+        self.estimation_variance = res['var'][inv]
+        self.status = res['status'][inv]
+        if neighbours:
+            idx = res['nbr_idx'].reshape(-1, self.ndmax).astype(np.int64)[inv]
+            self.neighbour_count = res['nbr_cnt'][inv]
+            self.candidates_tested = res['ncand'][inv]
+            self.neighbours = np.where(idx >= 0, s.sort_index[np.maximum(idx, 0)], -1)
+            self.neighbours_sorted_space = idx
+        self.timings['krige_s'] = time.time() - t0
+        self.timings['total_s'] = time.time() - t0 + self.timings.get('setup_s', 0.0)
+        if self.verbose:
+            print("Kriging Finished.")
+
+    def _launch_points(self, P, d, pt, n, out):
+        ptr = lambda t: C.c_void_p(None if t is None else t.data_ptr())
+        I = self._inputs_struct(d)
+        Q = _native.K3dPoints()
+        Q.npts = int(n)
+        Q.x, Q.y, Q.z, Q.ext, Q.start = ptr(pt['x']), ptr(pt['y']), ptr(pt['z']), ptr(pt['ext']), \
+            ptr(pt['start'])
+        Q.exclude_coincident = 1  # krige3d.py:359: option != 0
+        O = self._outputs_struct(out)
+        stream = torch.cuda.current_stream(self._device()).cuda_stream
+        _native.check(_native.lib().k3d_krige_points(C.byref(P), C.byref(I), C.byref(Q),
+                                                    C.byref(O), C.c_void_p(stream)))
+
     kriging = kt3d
 
     def write_output(self, path=None, unest=None):
         """Write `outfl`: Estimate and EstimationVariance, x fastest
-        (gslib_help/kt3d_help.md:37-41)."""
+        (gslib_help/kt3d_help.md:37-41); for `option` 1/2 one record per location:
+        X, Y, Z, True, Estimate, EstimationVariance, Error (estimate - true)."""
         if self.estimation is None:
             raise RuntimeError("run kt3d() first")
+        if self.koption != 0:
+            write_gslib_validation(path or self.outfl, self.locations, self.true_values,
+                                   self.estimation, self.estimation_variance, unest=unest)
+            return
         write_gslib_grid(path or self.outfl, self.estimation, self.estimation_variance,
                          unest=unest)
 

@@ -136,6 +136,20 @@ class SuperBlockSearcher(object):
         self.lutz, self.nodez0 = node_starts(self.zmn, self.zsiz, self.nz, self.zmnsup,
                                              self.zsizsup, self.nzsup)
 
+    def block_of_locations(self, x, y, z):
+        """getindx (super_block.py:319-346) for arbitrary locations: flat super-block index
+        of each (x, y, z), clamped to the network (the reference does not clamp; results
+        are only defined for locations inside the grid extent)."""
+        out = 0
+        mul = 1
+        for c, mn, siz, n in ((x, self.xmnsup, self.xsizsup, self.nxsup),
+                              (y, self.ymnsup, self.ysizsup, self.nysup),
+                              (z, self.zmnsup, self.zsizsup, self.nzsup)):
+            b = np.clip(bins_left(_edges_node(mn, siz, n), c), 0, n - 1)
+            out = out + b * mul
+            mul *= n
+        return out
+
     def pickup(self, device=None):
         """Search template (super_block.py:140-161, func_pickup :226-265) evaluated by
         the k3d_build_template kernel, then folded into x-runs on the host."""

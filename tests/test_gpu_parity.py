@@ -310,3 +310,121 @@ def test_host_buffer_c_abi_entry():
     # be ordered differently (covariance reuse); the values agree to rounding
     assert np.allclose(est, k.estimation, rtol=1e-11, atol=1e-12, equal_nan=True)
     assert np.allclose(var, k.estimation_variance, rtol=1e-11, atol=1e-12, equal_nan=True)
+
+
+# ---------------------------------------------------------------- option 1 / 2: listed locations
+def _oracle_points(par, data, px, py, pz, ext=None, koption=1):
+    names, cols = list(data.keys()), dict(data)
+    prop = [n for n in names if n not in ('x', 'y', 'z')]
+    st = orc.prepare(par, cols, prop)
+    return st, orc.run_points(st, px, py, pz, ext=ext, koption=koption, threads=8)
+
+
+def _compare_points(k, st, ores, vmax):
+    est, var, nbr, cnt = ores
+    assert np.array_equal(k.neighbour_count, cnt)
+    assert np.array_equal(k.neighbours_sorted_space, nbr.astype(np.int64))
+    assert np.array_equal(np.isnan(k.estimation), np.isnan(est))
+    ok = ~np.isnan(est)
+    derr = np.abs(k.estimation[ok] - est[ok])
+    assert np.all(derr <= EST_RTOL * np.abs(est[ok]) + 1e-12 * vmax), derr.max()
+    verr = np.abs(k.estimation_variance[ok] - var[ok])
+    assert np.all((verr <= VAR_RTOL * np.abs(var[ok])) | (verr <= VAR_ATOL)), verr.max()
+    return int(ok.sum())
+
+
+@pytest.mark.parametrize("name,scale", [("c3", 0.4), ("c2", 0.5), ("c4", 0.3)])
+def test_cross_validation_against_oracle(name, scale):
+    """option 1 (krige3d.py:200-208, 310-332, 359-363): every datum re-estimated from the
+    others.  c3 exercises the octant rule (the datum itself takes its place in its octant and
+    is dropped afterwards), c2 the plain ndmax rule, c4 the drift rows."""
+    from pygeostatistics_b200 import Krige3d
+    par, data, sec = k3d_configs.config(name, scale)
+    par = dict(par, option=1)
+    k = Krige3d(par, data=data)
+    k.verbose = False
+    k.kt3d(neighbours=True)
+    st, ores = _oracle_points(par, data, data['x'], data['y'], data['z'], koption=1)
+    n = _compare_points(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+    assert n > 0.9 * len(data['x'])
+    # a datum never appears among its own neighbours, and is not reproduced exactly
+    own = np.arange(len(data['x']))[:, None]
+    assert not (k.neighbours == own).any()
+    assert np.nanmax(np.abs(k.estimation - data['v'])) > 1e-3
+    assert np.array_equal(k.true_values, data['v'])
+    # the production path (no neighbour lists, unordered selection) gives the same numbers
+    k2 = Krige3d(par, data=data)
+    k2.verbose = False
+    k2.kt3d()
+    assert np.allclose(k2.estimation, k.estimation, rtol=1e-10, atol=1e-12, equal_nan=True)
+
+
+def test_jackknife_locations_and_grid_equivalence(tmp_path):
+    """option 2: estimation at the records of `jackfl`.  Locations on grid nodes must give
+    what the grid run gives there; arbitrary locations (some outside the grid: clamped to the
+    edge super block) must match the oracle; the file round trip works."""
+    from pygeostatistics_b200 import Krige3d
+    par, data, sec = k3d_configs.config("c3", 0.2)
+    nx, ny, nz = par['nx'], par['ny'], par['nz']
+    rng = np.random.default_rng(5)
+    idx = np.sort(rng.choice(nx * ny * nz, 3000, replace=False))
+    iz = idx // (nx * ny); iy = (idx - iz * nx * ny) // nx; ix = idx - iz * nx * ny - iy * nx
+    gx, gy, gz = par['xmn'] + ix * par['xsiz'], par['ymn'] + iy * par['ysiz'], par['zmn'] + iz * par['zsiz']
+    kg = gpu_run(par, data, sec)
+    jpar = dict(par, option=2)
+    kj = Krige3d(jpar, data=data, jackknife={'x': gx, 'y': gy, 'z': gz, 'v': np.zeros(len(gx))})
+    kj.verbose = False
+    kj.kt3d(neighbours=True)
+    assert np.array_equal(kj.neighbours, kg.neighbours[idx])
+    assert np.allclose(kj.estimation, kg.estimation[idx], rtol=1e-10, atol=1e-12, equal_nan=True)
+    assert np.allclose(kj.estimation_variance, kg.estimation_variance[idx], rtol=1e-9, atol=1e-12,
+                       equal_nan=True)
+    # arbitrary locations, a few outside the grid extent, a few on data
+    m = 4000
+    px = rng.uniform(-2.0, nx + 2.0, m); py = rng.uniform(-2.0, ny + 2.0, m); pz = rng.uniform(0.0, nz, m)
+    px[:50], py[:50], pz[:50] = data['x'][:50], data['y'][:50], data['z'][:50]
+    jk = {'x': px, 'y': py, 'z': pz, 'v': rng.normal(size=m)}
+    # through files: jackfl read by column name, outfl written per location
+    from pygeostatistics_b200.gslib_io import SpatialData
+    jf = tmp_path / "jack.dat"
+    with open(jf, "w") as f:
+        f.write("jack\n4\nx\ny\nz\nv\n")
+        for r in zip(px, py, pz, jk['v']):
+            f.write("\t".join(repr(float(c)) for c in r) + "\n")
+    fpar = dict(jpar, jackfl=str(jf), outfl=str(tmp_path / "xv.out"))
+    kf = Krige3d(fpar, data=data)
+    kf.verbose = False
+    kf.kt3d(neighbours=True)
+    # (the oracle gets the coordinates as the reader parsed them: pandas' default float
+    # parser, the one the reference uses, may differ from repr() in the last bit)
+    fx, fy, fz = kf.locations.T
+    st, ores = _oracle_points(jpar, data, fx, fy, fz, koption=2)
+    assert _compare_points(kf, st, ores, vmax=float(np.max(np.abs(data['v'])))) > 0.9 * m
+    # in memory: the 50 locations that ARE data lose that datum, octant slot included
+    km = Krige3d(jpar, data=data, jackknife=jk)
+    km.verbose = False
+    km.kt3d(neighbours=True)
+    st, ores = _oracle_points(jpar, data, px, py, pz, koption=2)
+    assert _compare_points(km, st, ores, vmax=float(np.max(np.abs(data['v'])))) > 0.9 * m
+    assert not (km.neighbours[:50] == np.arange(50)[:, None]).any()
+    kf.write_output()
+    out = SpatialData(str(tmp_path / "xv.out")).vr
+    assert out.dtype.names[:3] == ('X', 'Y', 'Z') and len(out) == m
+    # (the reader's float parser is pandas' fast one, exact to a few ulp)
+    assert np.allclose(out['Estimate'], kf.estimation, rtol=1e-12, atol=1e-14, equal_nan=True)
+    assert np.allclose(out['Error: est-true'], kf.estimation - jk['v'], rtol=1e-9, atol=1e-12,
+                       equal_nan=True)
+
+
+def test_cross_validation_ked_external_drift():
+    """option 1 with kriging with an external drift: the external value at each location
+    comes from the data's secondary column (krige3d.py:329-330)."""
+    from pygeostatistics_b200 import Krige3d
+    par, data, sec = k3d_configs.config("c5", 0.06)
+    par = dict(par, option=1, nxdis=1, nydis=1, nzdis=1)
+    k = Krige3d(par, data=data)
+    k.verbose = False
+    k.kt3d(neighbours=True)
+    names = [n for n in data if n not in ('x', 'y', 'z')]
+    st, ores = _oracle_points(par, data, data['x'], data['y'], data['z'], ext=data[names[1]], koption=1)
+    assert _compare_points(k, st, ores, vmax=float(np.max(np.abs(data[names[0]])))) > 0.5 * len(data['x'])

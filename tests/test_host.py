@@ -63,7 +63,7 @@ def test_param_file_and_checks(tmp_path):
     for bad, exc in ((dict(radius_hmax=0), ValueError), (dict(nst=0), ValueError),
                      (dict(it=[7]), ValueError), (dict(it=[4], aa_hmax=[2.5]), ValueError),
                      (dict(idrift=[0] * 9), ValueError), (dict(ikrige=3, icolsec=0), ValueError),
-                     (dict(ndmax=65), ValueError), (dict(option=1), NotImplementedError)):
+                     (dict(ndmax=65), ValueError), (dict(option=3), ValueError)):
         with pytest.raises(exc):
             Krige3d(dict(par, **bad), data={'x': np.zeros(2), 'y': np.zeros(2), 'v': np.zeros(2)})
     missing = dict(par)
@@ -269,3 +269,26 @@ def test_plane_runs_cut_at_super_block_boundaries():
         assert all(a[1] == b[0] for a, b in zip(runs[:-1], runs[1:]))
         assert all(a < b for a, b in runs)
         assert all(b in _S.nodez0 for _, b in runs[:-1])
+
+
+def test_block_of_locations_equals_oracle_getindx():
+    """Super block of arbitrary locations (getindx, super_block.py:319-346): host set-up
+    and oracle agree, also on edges and outside the network (both clamp)."""
+    from oracle import kt3d_oracle as orc
+    par, data, sec = k3d_configs.config("c3", 0.2)
+    st = orc.prepare(par, dict(data), ['v'])
+    k = Krige3d(par, data=data)
+    k._preprocess()
+    s = SuperBlockSearcher()
+    s.nx, s.xmn, s.xsiz, s.ny, s.ymn, s.ysiz = k.nx, k.xmn, k.xsiz, k.ny, k.ymn, k.ysiz
+    s.nz, s.zmn, s.zsiz, s.vr, s.MAXSB = k.nz, k.zmn, k.zsiz, k.vr, k.const.MAXSB
+    s.setup()
+    rng = np.random.default_rng(3)
+    m = 5000
+    px = rng.uniform(-3, par['nx'] + 3, m); py = rng.uniform(-3, par['ny'] + 3, m)
+    pz = rng.uniform(-3, par['nz'] + 3, m)
+    edges = st['node_edges'][0]
+    px[:len(edges)] = edges
+    sb = orc.super_block_of(st, px, py, pz)
+    flat = sb[:, 0] + sb[:, 1] * s.nxsup + sb[:, 2] * s.nxsup * s.nysup
+    assert np.array_equal(s.block_of_locations(px, py, pz), flat)

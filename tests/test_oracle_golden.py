@@ -158,3 +158,29 @@ def test_small_full_runs_match_unmodified_reference(golden_dir, name):
     scale = max(1.0, np.max(np.abs(g['est'][ok])))
     assert np.max(np.abs(est[ok] - g['est'][ok])) < 1e-10 * scale
     assert np.max(np.abs(var[ok] - g['var'][ok])) < 1e-10 * max(1.0, np.max(np.abs(g['var'][ok])))
+
+
+def test_oracle_locations_mode_properties():
+    """Cross-validation / jackknife restatement (krige3d.py:310-332, 359-363; the reference
+    crashes there, D11 -- parity unpinned by the reference): at grid nodes it IS the grid
+    loop; at the data it interpolates exactly unless the datum is excluded."""
+    import k3d_configs
+    par, data, sec = k3d_configs.config("c3", 0.2)
+    st = orc.prepare(par, dict(data), ['v'])
+    nx, ny, nz = par['nx'], par['ny'], par['nz']
+    idx = np.arange(0, nx * ny * nz, 11)
+    iz = idx // (nx * ny); iy = (idx - iz * nx * ny) // nx; ix = idx - iz * nx * ny - iy * nx
+    px = par['xmn'] + ix * par['xsiz']; py = par['ymn'] + iy * par['ysiz']; pz = par['zmn'] + iz * par['zsiz']
+    a = orc.run(st, node_list=idx, threads=4)
+    for kopt in (0, 2):  # no datum sits on a node of this grid: exclusion changes nothing
+        b = orc.run_points(st, px, py, pz, koption=kopt, threads=4)
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v, equal_nan=True)
+    x, y, z, v = data['x'], data['y'], data['z'], data['v']
+    e0, v0, n0, c0 = orc.run_points(st, x, y, z, koption=0, threads=4)
+    assert np.max(np.abs(e0 - v)) < 1e-9 and np.max(np.abs(v0)) < 1e-9
+    e1, v1, n1, c1 = orc.run_points(st, x, y, z, koption=1, threads=4)
+    srt = np.argsort(st['sort_index'])           # original row -> sorted position
+    assert not (n1 == srt[:, None]).any()        # never its own neighbour
+    assert np.nanmin(v1) > 1e-3 and np.nanmax(np.abs(e1 - v)) > 1e-2
+    assert np.all(c1 <= par['ndmax'])
