@@ -773,6 +773,9 @@ __device__ __forceinline__ void snake_node(const Tile &T, int t, int &lx, int &l
 //                                 by (distance, index) and -1 padded when `ordered`
 //   cnt[node - slab]              number of neighbours, min(nclose, ndmax)
 // ---------------------------------------------------------------------------
+// PTS: estimation at listed locations (K3dPoints) instead of grid nodes -- a separate
+// instantiation, so that the grid kernel carries none of the coincident-sample logic
+template <bool PTS>
 __global__ void __launch_bounds__(256, 4)
 k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const int iz0,
                   const int iz1, int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
@@ -798,7 +801,9 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
 
     __shared__ int s_total, s_warpsum[32];
 
-    const Tile T = tile_of_block(P, in, iz0, iz1, pts);
+    const PtSet nopts = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    const PtSet &geo = PTS ? pts : nopts; // (folds to grid mode at compile time)
+    const Tile T = tile_of_block(P, in, iz0, iz1, geo);
     if (T.tnodes <= 0)
         return;
     const int sbx = T.sbx, sby = T.sby, sbz = T.sbz;
@@ -870,7 +875,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     nc.qx = staged ? stx : in.sx;
     nc.qy = staged ? sty : in.sy;
     nc.qz = staged ? stz : in.sz;
-    nc.excl = pts.x ? pts.exclude : 0;
+    nc.excl = PTS ? pts.exclude : 0;
 
     // ---- each warp walks a contiguous piece of a boustrophedon path through the tile:
     //      consecutive nodes are grid neighbours, so their neighbourhoods overlap ---------
@@ -885,7 +890,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     int nsubw = -1; // length of sub[], or -1: scan every staged candidate
     if (staged && t_begin < t_end) {
         double bcx, bcy, bcz, ex, ey, ez; // centre and half extents of the walk's bounding box
-        if (pts.x) {
+        if (PTS) {
             double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
             for (int t = t_begin + lane; t < t_end; t += 32) {
                 const size_t q = (size_t)(T.first + t);
@@ -947,7 +952,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     }
 
     for (int t = t_begin; t < t_end; t++) {
-        const NodeLoc L = node_of_tile(P, T, pts, t, slab_off);
+        const NodeLoc L = node_of_tile(P, T, geo, t, slab_off);
         const size_t o = L.o;
         nc.xloc = L.x; nc.yloc = L.y; nc.zloc = L.z;
         int tested = 0;
@@ -1183,13 +1188,13 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             solve = true;
         }
         const int N = na + mdt, R = N + 1;
+        int nnew = na;    // newcomers among the neighbours
+        bool full = true; // the whole system is rebuilt (no reuse of the previous node's)
         if (solve) {
             // ---- 1. map the neighbours to matrix positions ---------------------------
             // A neighbour kept from the previous node keeps its row/column, so the
             // sample-sample covariances already in Pm stay valid; newcomers take the
             // positions that were freed.  (newpos[], newid[]) lists what must be filled.
-            int nnew = na;
-            bool full = true;
             if (cfg.reuse && nprev == na && na <= 32) {
                 int pos = -1;
                 const int myid = lane < na ? nbr[o * P.ndmax + lane] : -1;
@@ -1228,17 +1233,22 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 if (has_ext) ve[pos] = e;
                 transform_point(P, Q, x - cx0, y - cy0, z - cz0, ut, ustride, pos);
             }
-            // the node and its block points in every structure's coordinates (columns ndp..)
-            if (lane == 0)
-                transform_point_cold(P, Q, xloc - cx0, yloc - cy0, zloc - cz0, unode, 1, 0);
-            __syncwarp();
+            // the node and its block points in every structure's coordinates (records
+            // ndp..): lane 4*s + k computes component k of structure s
+            double un = 0.0;
+            if (lane < ustride && (lane & 3) < 3) {
+                const double *r = Q.rs[lane >> 2] + 3 * (lane & 3);
+                un = r[0] * (xloc - cx0) + r[1] * (yloc - cy0) + r[2] * (zloc - cz0);
+            }
             if constexpr (BLOCK) {
+                if (lane < ustride) unode[lane] = un;
+                __syncwarp();
                 for (int k = lane; k < ustride * P.ndb; k += 32) {
                     const int j = k / ustride, row = k - j * ustride;
                     ut[(ndp + j) * ustride + row] = unode[row] + udb[j * ustride + row];
                 }
             } else {
-                if (lane < ustride) ut[ndp * ustride + lane] = unode[lane] + udb[lane];
+                if (lane < ustride) ut[ndp * ustride + lane] = un + udb[lane];
             }
             __syncwarp();
 
@@ -1431,55 +1441,71 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 var = P.cbb - sw * cb;
                 nprev = -1;
             } else {
-                // data vector and constraint rows (krige3d.py:764-767, 493-583 with repair
-                // D6): they depend on the node and are rebuilt every time
-                for (int i = lane; i < na; i += 32) {
-                    const double x = px[i] - xloc, y = py[i] - yloc, z = pz[i] - zloc;
-                    const int ri = R - i;
-                    Pm[pk(ri, ri)] = P.maxcov; // cova3(p, p)
-                    Pm[pk(ri, 0)] = va[i];     // v row
-                    if (nsplit > 1) { // b row from the partial sums (krige3d.py:797-798)
-                        double cb = 0.0;
-                        for (int q = 0; q < nsplit; q++) cb += part[q * napad_max + i];
-                        Pm[pk(ri, 1)] = cb / (double)P.ndb;
+                // Border of the system (krige3d.py:764-767, 493-583 with repair D6).  What
+                // only depends on the neighbours' positions -- diagonal, data vector,
+                // unbiasedness row, constraint block -- stays in Pm from node to node and is
+                // written on a full rebuild (newcomers refresh their data-vector entry);
+                // what depends on the node -- drift monomials, external drift, the block
+                // right-hand side -- is rebuilt every time.
+                const bool drift = mdt > 1;
+                if (full) {
+                    for (int i = lane; i < na; i += 32) {
+                        const int ri = R - i;
+                        Pm[pk(ri, ri)] = P.maxcov; // cova3(p, p)
+                        Pm[pk(ri, 0)] = va[i];     // v row
+                        if (mdt > 0) Pm[pk(ri, R - na)] = P.unbias;
                     }
-                    if (P.itrend) Pm[pk(ri, 1)] = 0.0; // repair D10: kriging the trend
-                    if (mdt > 0) {
+                    if (lane == 0) {
+                        for (int q1 = na; q1 < N; q1++)
+                            for (int q2 = q1; q2 < N; q2++)
+                                Pm[pk(R - q1, R - q2)] = 0.0;
                         int q = na;
-                        Pm[pk(ri, R - q)] = P.unbias;
-                        q++;
+                        if (mdt > 0) {
+                            Pm[pk(R - q, 1)] = P.unbias; Pm[pk(R - q, 0)] = 0.0; q++;
+                            for (int l = 0; l < K3D_MAXDRIFT; l++)
+                                if (P.idrift[l]) { Pm[pk(R - q, 1)] = P.bv[l]; Pm[pk(R - q, 0)] = 0.0; q++; }
+                            if (P.ktype == 3) { Pm[pk(R - q, 0)] = 0.0; q++; }
+                        }
+                        Pm[2] = P.cbb; // (b,b): block covariance
+                        Pm[1] = 0.0;   // (v,b): becomes -estimate
+                        Pm[0] = 0.0;   // (v,v): unused
+                    }
+                } else {
+                    for (int k = lane; k < nnew; k += 32) {
+                        const int pos = newpos[k];
+                        Pm[pk(R - pos, 0)] = va[pos];
+                    }
+                }
+                if (nsplit > 1 || P.itrend || drift) {
+                    for (int i = lane; i < na; i += 32) {
+                        const int ri = R - i;
+                        if (nsplit > 1) { // b row from the partial sums (krige3d.py:797-798)
+                            double cb = 0.0;
+                            for (int q = 0; q < nsplit; q++) cb += part[q * napad_max + i];
+                            Pm[pk(ri, 1)] = cb / (double)P.ndb;
+                        }
+                        if (P.itrend) Pm[pk(ri, 1)] = 0.0; // repair D10: kriging the trend
+                        if (drift) {
+                            const double x = px[i] - xloc, y = py[i] - yloc, z = pz[i] - zloc;
+                            int q = na + 1;
 #pragma unroll
-                        for (int l = 0; l < K3D_MAXDRIFT; l++) {
-                            if (P.idrift[l]) {
-                                double f = l == 0 ? x : l == 1 ? y : l == 2 ? z
-                                         : l == 3 ? x * x : l == 4 ? y * y : l == 5 ? z * z
-                                         : l == 6 ? x * y : l == 7 ? x * z : y * z;
-                                Pm[pk(ri, R - q)] = f * P.resc;
+                            for (int l = 0; l < K3D_MAXDRIFT; l++) {
+                                if (P.idrift[l]) {
+                                    double f = l == 0 ? x : l == 1 ? y : l == 2 ? z
+                                             : l == 3 ? x * x : l == 4 ? y * y : l == 5 ? z * z
+                                             : l == 6 ? x * y : l == 7 ? x * z : y * z;
+                                    Pm[pk(ri, R - q)] = f * P.resc;
+                                    q++;
+                                }
+                            }
+                            if (P.ktype == 3) {
+                                Pm[pk(ri, R - q)] = ve[i] * resce;
                                 q++;
                             }
                         }
-                        if (P.ktype == 3) {
-                            Pm[pk(ri, R - q)] = ve[i] * resce;
-                            q++;
-                        }
                     }
                 }
-                // constraint block (zeros), its right-hand sides, and the border corner
-                if (lane == 0) {
-                    for (int q1 = na; q1 < N; q1++)
-                        for (int q2 = q1; q2 < N; q2++)
-                            Pm[pk(R - q1, R - q2)] = 0.0;
-                    int q = na;
-                    if (mdt > 0) {
-                        Pm[pk(R - q, 1)] = P.unbias; Pm[pk(R - q, 0)] = 0.0; q++;
-                        for (int l = 0; l < K3D_MAXDRIFT; l++)
-                            if (P.idrift[l]) { Pm[pk(R - q, 1)] = P.bv[l]; Pm[pk(R - q, 0)] = 0.0; q++; }
-                        if (P.ktype == 3) { Pm[pk(R - q, 1)] = extest * resce; Pm[pk(R - q, 0)] = 0.0; q++; }
-                    }
-                    Pm[2] = P.cbb; // (b,b): block covariance
-                    Pm[1] = 0.0;   // (v,b): becomes -estimate
-                    Pm[0] = 0.0;   // (v,v): unused
-                }
+                if (P.ktype == 3 && lane == 0) Pm[pk(R - (N - 1), 1)] = extest * resce; // last constraint
                 __syncwarp();
 
                 // ---- 3. LDL^T elimination of the N pivots ---------------------------
@@ -1807,7 +1833,9 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
     if (ntiles > 0x7fffffffLL) return fail(K3D_EINVAL, "too many tiles");
     KPrep q;
     make_prep(p, &q);
-    CUDA_TRY(cudaFuncSetAttribute(k3d_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(k3d_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  sc.smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k3d_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   sc.smem_bytes));
 
     // neighbour lists travel from the search kernel to the solve kernel through global
@@ -1858,8 +1886,12 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
         int32_t *nbr = co.nbr_idx ? co.nbr_idx : snbr;
         int32_t *cnt = co.nbr_cnt ? co.nbr_cnt : scnt;
         cudaEventRecord(g_ev[0], st);
-        k3d_search_kernel<<<(unsigned)ntiles, sc.warps * 32, sc.smem_bytes, st>>>(
-            *p, ci, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc, ps);
+        if (pts)
+            k3d_search_kernel<true><<<(unsigned)ntiles, sc.warps * 32, sc.smem_bytes, st>>>(
+                *p, ci, 0, p->nz, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc, ps);
+        else
+            k3d_search_kernel<false><<<(unsigned)ntiles, sc.warps * 32, sc.smem_bytes, st>>>(
+                *p, ci, za, zb, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc, ps);
         if (cudaGetLastError() != cudaSuccess) { rc = fail(K3D_ECUDA, "search kernel launch failed"); break; }
         cudaEventRecord(g_ev[1], st);
         switch (amax_for(bc.rtot)) {
