@@ -96,8 +96,10 @@ struct BCfg {       // solve kernel
     int reuse;      // 1: keep the sample-sample covariance block between adjacent nodes
     int nsplit;     // block kriging: work items per sample of the right-hand side
     int napad;      // ndmax rounded up to a multiple of 32
-    int ustride;    // doubles per point in structure space: 4 per structure (x, y, z, pad)
+    int ustride;    // doubles per point in structure space: 4 per structure (x, y, z, pad) + 2,
+                    // which spreads consecutive records over all shared-memory banks
     int has_ext;    // 1: external-drift values of the neighbours are kept (ktype 2/3)
+    int need_xyz;   // 1: neighbour coordinates are kept (drift monomials, block kriging)
     int pw_bytes;   // per-warp shared bytes
     int smem_bytes; // total dynamic shared bytes
 };
@@ -136,10 +138,11 @@ __host__ __device__ inline int spw_bytes(const SCfg &c) { return align16(spw_off
 //   CTA : [tri LUT u16 x ntri][block points per structure f64 x 3*nst*ndb]
 //         [round table u16 x warps*rounds_per_warp]
 //   warp: [P f64 x ntri]                        pristine bordered system (persists)
-//         [px,py,pz,va(,ve) f64 x ndp]          neighbours by matrix position (ve: ktype 2/3)
+//         [va(,px,py,pz)(,ve) f64 x ndp]        neighbours by matrix position (coordinates:
+//                                               drift / block kriging only; ve: ktype 2/3)
 //         [ut f64 x ustride*(ndp+ndb)]          their coordinates in structure space (one
-//                                               record of nst x (x, y, z, pad) per point), then
-//                                               the node's block points (records ndp..)
+//                                               record of nst x (x, y, z, pad) + 2 pad per
+//                                               point), then the node's block points (ndp..)
 //         [pid,newid i32 x ndp][newpos u8 x ndp] sample id by position / fill list
 //         [pivot rows f64 x 2*urow]              the node's structure-space record (unode,
 //                                               ustride doubles, set-up phase only) shares it
@@ -152,7 +155,7 @@ __host__ __device__ inline int b_rounds_per_warp(const BCfg &c)
 __host__ __device__ inline int b_off_rtab(const BCfg &c) { return align16(b_off_udb(c) + c.ustride * c.ndb * 8); }
 __host__ __device__ inline int b_off_warp(const BCfg &c) { return align16(b_off_rtab(c) + c.warps * b_rounds_per_warp(c) * 2); }
 __host__ __device__ inline int bpw_off_pos(const BCfg &c) { return align16(c.ntri * 8); }
-__host__ __device__ inline int bpw_off_ut(const BCfg &c) { return bpw_off_pos(c) + (4 + c.has_ext) * c.ndp * 8; }
+__host__ __device__ inline int bpw_off_ut(const BCfg &c) { return bpw_off_pos(c) + (1 + 3 * c.need_xyz + c.has_ext) * c.ndp * 8; }
 __host__ __device__ inline int bpw_off_ints(const BCfg &c) { return bpw_off_ut(c) + c.ustride * (c.ndp + c.ndb) * 8; }
 __host__ __device__ inline int bpw_off_rows(const BCfg &c) { return align16(bpw_off_ints(c) + 9 * c.ndp); }
 __host__ __device__ inline int bpw_off_part(const BCfg &c)
@@ -162,7 +165,7 @@ __host__ __device__ inline int bpw_off_part(const BCfg &c)
 }
 __host__ __device__ inline int bpw_bytes(const BCfg &c)
 {
-    return align16(bpw_off_part(c) + (c.nsplit > 1 ? c.nsplit * c.napad * 8 : 0));
+    return align16(bpw_off_part(c) + (c.ndb > 1 ? c.nsplit * c.napad * 8 : 0));
 }
 
 // ---------------------------------------------------------------------------
@@ -295,21 +298,6 @@ __device__ __forceinline__ double cova_term(const K3dParams &P, const KPrep &Q, 
     return c * cos(sqrt(h2) * 3.141592653589793);
 }
 
-__device__ __forceinline__ double cova_from_h2(const K3dParams &P, const KPrep &Q,
-                                               const double (&h2v)[K3D_MAXNST],
-                                               const double *__restrict__ exptab)
-{
-    if (h2v[0] < Q.eps0s)
-        return P.maxcov;
-    double cova = 0.0;
-#pragma unroll 1
-    for (int s = 0; s < P.nst; s++) {
-        const double h2 = s == 0 ? h2v[0] : s == 1 ? h2v[1] : s == 2 ? h2v[2] : h2v[3];
-        cova += cova_term(P, Q, s, h2, exptab);
-    }
-    return cova;
-}
-
 // u = rs[s] * (x,y,z) for every structure, written as record idx (4 doubles per structure:
 // x, y, z, pad; records `stride` doubles apart)
 __device__ __forceinline__ void transform_point(const K3dParams &P, const KPrep &Q, double x,
@@ -353,16 +341,16 @@ template <int AMAX> struct RegSolve {
                                                   int li, int lj, double ninv)
     {
         constexpr int B = ((4 * (A - 1) + 3) >> 3) + 1;
-        double w[A], u[B];
-#pragma unroll
-        for (int a = 0; a < A; a++) w[a] = row[li + 4 * a];
+        double u[B];
 #pragma unroll
         for (int b = 0; b < B; b++) u[b] = row[lj + 8 * b] * ninv;
 #pragma unroll
-        for (int a = 0; a < A; a++)
+        for (int a = 0; a < A; a++) {
+            const double w = row[li + 4 * a]; // one at a time: registers are the limit
 #pragma unroll
             for (int b = 0; b < B; b++)
-                if (8 * b <= 4 * a + 3) m[a][b] = fma(w[a], u[b], m[a][b]);
+                if (8 * b <= 4 * a + 3) m[a][b] = fma(w, u[b], m[a][b]);
+        }
     }
 
     // Pivots M = 4*AP+3 .. 4*AP (those that exist).  Their rows live in register block AP
@@ -1073,7 +1061,11 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
 // BLOCK: block kriging (ndb > 1), whose right-hand side averages over the block points;
 // point kriging takes a leaner covariance loop driven by per-warp work-item lists.
 template <int AMAX, bool BLOCK>
+#ifdef K3D_REG80
+__global__ void __launch_bounds__(AMAX == 5 || AMAX == 9 ? 256 : 640, AMAX == 5 || AMAX == 9 ? K3D_SMALL_CTAS : 1)
+#else
 __global__ void __launch_bounds__(AMAX == 5 ? 256 : 640, AMAX == 5 ? K3D_SMALL_CTAS : 1)
+#endif
 k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
                  const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
                  const int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
@@ -1090,8 +1082,9 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
               o_ut = bpw_off_ut(cfg), o_ints = bpw_off_ints(cfg), o_part = bpw_off_part(cfg);
     unsigned char *wbase = smem + o_warp0 + warp * pwb;
     double *Pm = (double *)wbase;
-    double *px = (double *)(wbase + o_pos);
-    double *py = px + ndp, *pz = py + ndp, *va = pz + ndp, *ve = va + ndp; // ve: has_ext only
+    // [va][px,py,pz: need_xyz only][ve: has_ext only]
+    double *va = (double *)(wbase + o_pos);
+    double *px = va + ndp, *py = px + ndp, *pz = py + ndp, *ve = va + (1 + 3 * cfg.need_xyz) * ndp;
     double *ut = (double *)(wbase + o_ut);
     int *pid = (int *)(wbase + o_ints);
     int *newid = pid + ndp;
@@ -1102,7 +1095,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     double *part = (double *)(wbase + o_part);
 
     __shared__ double s_exptab[32];  // 2^(j/32)
-    __shared__ int s_job[20][6];     // per warp: npairs, npad, na, full, R, magic
+    __shared__ int s_job[20];        // per warp: R | na << 8 | pair rounds << 16 | full << 24
     __shared__ int s_nrounds[2];     // rounds of 32 covariance items published (by parity of tt)
     unsigned short *s_rtab = (unsigned short *)(smem + b_off_rtab(cfg)); // (warp << 8) | round
     __shared__ double s_jloc[20][3]; // per warp: node location
@@ -1198,8 +1191,15 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             if (cfg.reuse && nprev == na && na <= 32) {
                 int pos = -1;
                 const int myid = lane < na ? nbr[o * P.ndmax + lane] : -1;
-                for (int p = 0; p < na; p++)
-                    if (pid[p] == myid) pos = p;
+                // (four positions per shared-memory load; entries beyond na are stale)
+                const int4 *pid4 = reinterpret_cast<const int4 *>(pid);
+                for (int p = 0; p < na; p += 4) {
+                    const int4 v = pid4[p >> 2];
+                    if (v.x == myid) pos = p;
+                    if (v.y == myid && p + 1 < na) pos = p + 1;
+                    if (v.z == myid && p + 2 < na) pos = p + 2;
+                    if (v.w == myid && p + 3 < na) pos = p + 3;
+                }
                 if (lane >= na) pos = -2;
                 const unsigned used = __reduce_or_sync(FULL, pos >= 0 ? (1u << pos) : 0u);
                 const unsigned unm = __ballot_sync(FULL, pos == -1);
@@ -1227,7 +1227,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 const int pos = newpos[k], g = newid[k];
                 pid[pos] = g;
                 const double x = in.sx[g], y = in.sy[g], z = in.sz[g];
-                px[pos] = x; py[pos] = y; pz[pos] = z;
+                if (cfg.need_xyz) { px[pos] = x; py[pos] = y; pz[pos] = z; }
                 const double v = in.sv[g], e = has_ext ? in.ssec[g] : 0.0;
                 va[pos] = (P.ktype == 0) ? v - P.skmean : (P.ktype == 2 ? v - e : v);
                 if (has_ext) ve[pos] = e;
@@ -1236,7 +1236,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             // the node and its block points in every structure's coordinates (records
             // ndp..): lane 4*s + k computes component k of structure s
             double un = 0.0;
-            if (lane < ustride && (lane & 3) < 3) {
+            if (lane < 4 * P.nst && (lane & 3) < 3) {
                 const double *r = Q.rs[lane >> 2] + 3 * (lane & 3);
                 un = r[0] * (xloc - cx0) + r[1] * (yloc - cy0) + r[2] * (zloc - cz0);
             }
@@ -1252,32 +1252,20 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             }
             __syncwarp();
 
-            // publish this warp's covariance job for the pooled phase: its parameters and
-            // one round-table entry per 32 work items
+            // publish this warp's covariance job for the pooled phase: one job word and one
+            // round-table entry per round of 32 work items.  Pair rounds: one per newcomer
+            // (lane = the other position), or the whole triangle 32 pairs at a time; then the
+            // right-hand side: lane = sample, one round per part of the block discretisation
             {
                 const int npairs = full ? (na * (na - 1)) >> 1 : nnew * na;
-                int nr;
-                if constexpr (BLOCK) {
-                    const int npad = (npairs + 31) & ~31;  // pairs, padded to whole rounds
-                    nr = (npad + nsplit * ((na + 31) & ~31)) >> 5;
-                    if (lane == 0) {
-                        s_job[warp][0] = npairs;
-                        s_job[warp][1] = npad;
-                        s_job[warp][2] = na;
-                        s_job[warp][3] = full ? 1 : 0;
-                        s_job[warp][5] = (65536 + na - 1) / na;
-                        s_jloc[warp][0] = xloc; s_jloc[warp][1] = yloc; s_jloc[warp][2] = zloc;
-                    }
-                } else {
-                    // pair rounds: one per newcomer (lane = the other position), or the
-                    // whole triangle 32 pairs at a time; then the right-hand side
-                    const int npr = full ? (npairs + 31) >> 5 : nnew;
-                    nr = npr + ((na + 31) >> 5);
-                    if (lane == 0) s_job[warp][0] = R | (na << 8) | (npr << 16) | (full ? 1 << 24 : 0);
-                }
+                const int npr = full ? (npairs + 31) >> 5 : nnew;
+                const int nr = npr + nsplit * ((na + 31) >> 5);
                 int base = 0;
                 if (lane == 0) {
-                    if constexpr (BLOCK) s_job[warp][4] = R;
+                    s_job[warp] = R | (na << 8) | (npr << 16) | (full ? 1 << 24 : 0);
+                    if constexpr (BLOCK) {
+                        s_jloc[warp][0] = xloc; s_jloc[warp][1] = yloc; s_jloc[warp][2] = zloc;
+                    }
                     base = atomicAdd(&s_nrounds[tt & 1], nr);
                 }
                 base = __shfl_sync(FULL, base, 0);
@@ -1288,149 +1276,98 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         K3D_PHASE_BARRIER();
 
         // ---- 2. covariances of every node in flight, pooled over the CTA ---------------
-        // One work loop evaluates every covariance the nodes need (krige3d.py:748-801); the
-        // items of all warps are dealt out evenly, 32 at a time, so that no warp waits for
-        // another's longer list.  Per warp (job):
-        //   items [0, npairs)           sample-sample pairs: all, or those with a newcomer
-        //   items [npad, npad + ...)    sample i against (a part of) the node's block points
+        // One work loop evaluates every covariance the nodes need (krige3d.py:748-801,
+        // 838-875); the rounds of all warps are dealt out evenly, so that no warp waits for
+        // another's longer list.  One item = the covariance between two records of the job's
+        // structure-space table: two samples (pair rounds), or a sample and the node's block
+        // points (right-hand side rounds; record ndp.. = the node).
         {
             const int nrounds = s_nrounds[tt & 1];
-            if constexpr (!BLOCK) {
-                // point kriging: one item = the covariance between two records of the job's
-                // structure-space table (krige3d.py:748-801, 838-875); a round is either 32
-                // sample pairs or the right-hand side of up to 32 samples (record ndp = node)
-                const uint32_t a_rtab = smem_u32(s_rtab), a_w0 = smem_u32(smem + o_warp0),
-                               a_job = smem_u32(&s_job[0][0]), a_tri = smem_u32(tri);
-                const int o_newpos = o_ints + 8 * ndp;
-                for (int e = warp; e < nrounds; e += cfg.warps) {
-                    const int ent = lds_u16(a_rtab + 2 * e);
-                    const int jw = ent >> 8, r = ent & 255;
-                    const uint32_t jb = a_w0 + jw * pwb;
-                    const int job = lds_s32(a_job + jw * (int)sizeof(s_job[0]));
-                    const int jR = job & 255, jna = (job >> 8) & 255, npr = (job >> 16) & 255;
-                    // idle lanes repeat the last item of their kind (same value, same place)
-                    const bool rhs = r >= npr;
-                    int p1, p2r;
-                    if (rhs) {
-                        p1 = min(((r - npr) << 5) + lane, jna - 1);
-                        p2r = ndp;
-                    } else if (job >> 24) {
-                        const int w = min((r << 5) + lane, ((jna * (jna - 1)) >> 1) - 1);
-                        const int rc = lds_u16(a_tri + 2 * w);
-                        p1 = rc & 255;
-                        p2r = (rc >> 8) + 1;
+            const uint32_t a_rtab = smem_u32(s_rtab), a_w0 = smem_u32(smem + o_warp0),
+                           a_job = smem_u32(&s_job[0]), a_tri = smem_u32(tri);
+            const int o_newpos = o_ints + 8 * ndp;
+            for (int e = warp; e < nrounds; e += cfg.warps) {
+                const int ent = lds_u16(a_rtab + 2 * e);
+                const int jw = ent >> 8, r = ent & 255;
+                const uint32_t jb = a_w0 + jw * pwb;
+                const int job = lds_s32(a_job + 4 * jw);
+                const int jR = job & 255, jna = (job >> 8) & 255, npr = (job >> 16) & 255;
+                // idle lanes repeat the last item of their kind (same value, same place)
+                const bool rhs = r >= npr;
+                int p1, p2r, prt = 0, nsub = 1;
+                if (rhs) {
+                    int rr = r - npr;
+                    if constexpr (BLOCK) { // part prt of the block points, 32 samples per round
+                        const int ngr = (jna + 31) >> 5;
+                        prt = ngr == 1 ? rr : rr / ngr;
+                        rr -= prt * ngr;
+                        const int sub0 = (prt * P.ndb) / nsplit;
+                        nsub = ((prt + 1) * P.ndb) / nsplit - sub0;
+                        p2r = ndp + sub0;
                     } else {
-                        int pn;
-                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pn) : "r"(jb + o_newpos + r));
-                        const int q = min(lane, jna - 1);
-                        p1 = min(pn, q);
-                        p2r = max(pn, q);
+                        p2r = ndp;
                     }
-                    uint32_t a1 = jb + o_ut + p1 * (ustride << 3);
-                    uint32_t a2 = jb + o_ut + p2r * (ustride << 3);
+                    p1 = min((rr << 5) + lane, jna - 1);
+                } else if (job >> 24) {
+                    const int w = min((r << 5) + lane, ((jna * (jna - 1)) >> 1) - 1);
+                    const int rc = lds_u16(a_tri + 2 * w);
+                    p1 = rc & 255;
+                    p2r = (rc >> 8) + 1;
+                } else {
+                    int pn;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pn) : "r"(jb + o_newpos + r));
+                    const int q = min(lane, jna - 1);
+                    p1 = min(pn, q);
+                    p2r = max(pn, q);
+                }
+                const uint32_t a1 = jb + o_ut + p1 * (ustride << 3);
+                uint32_t a2 = jb + o_ut + p2r * (ustride << 3);
+                double relx = 0.0, rely = 0.0, relz = 0.0; // sample - node (block kriging)
+                if constexpr (BLOCK) {
+                    if (rhs) {
+                        const double *jpx = (const double *)(smem + o_warp0 + jw * pwb + o_pos) + ndp;
+                        relx = jpx[p1] - s_jloc[jw][0];
+                        rely = jpx[ndp + p1] - s_jloc[jw][1];
+                        relz = jpx[2 * ndp + p1] - s_jloc[jw][2];
+                    }
+                }
+                double acc = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < nsub; k++, a2 += ustride << 3) {
                     double c = 0.0;
                     bool zero = false;
+                    uint32_t b1 = a1, b2 = a2;
 #pragma unroll 1
-                    for (int st = 0; st < P.nst; st++, a1 += 32, a2 += 32) {
-                        const double2 u = lds_f64x2(a1), v = lds_f64x2(a2);
-                        const double uz = lds_f64(a1 + 16), vz = lds_f64(a2 + 16);
+                    for (int st = 0; st < P.nst; st++, b1 += 32, b2 += 32) {
+                        const double2 u = lds_f64x2(b1), v = lds_f64x2(b2);
+                        const double uz = lds_f64(b1 + 16), vz = lds_f64(b2 + 16);
                         const double dx = u.x - v.x, dy = u.y - v.y, dz = uz - vz;
                         const double h2 = dx * dx + dy * dy + dz * dz;
                         if (st == 0) zero = h2 < Q.eps0s;
                         c += cova_term(P, Q, st, h2, s_exptab);
                     }
                     if (zero) c = P.maxcov; // krige3d.py:853-855
-                    const int ri = jR - p1;
-                    sts_f64(jb + (pk(ri, rhs ? 1 : jR - p2r) << 3), c);
-                }
-            } else {
-            for (int e = warp; e < nrounds; e += cfg.warps) {
-                const int ent = s_rtab[e];
-                const int jw = ent >> 8;
-                const int jnpad = s_job[jw][1], jna = s_job[jw][2];
-                const int jnapad = (jna + 31) & ~31;
-                {
-                    const int jnpairs = s_job[jw][0], jfull = s_job[jw][3], jR = s_job[jw][4];
-                    const int magic = s_job[jw][5];
-                    unsigned char *jb = smem + o_warp0 + jw * pwb;
-                    double *jPm = (double *)jb;
-                    const double *jpx = (const double *)(jb + o_pos);
-                    const double *jpy = jpx + ndp, *jpz = jpy + ndp;
-                    const double *jut = (const double *)(jb + o_ut);
-                    const unsigned char *jnewpos = (const unsigned char *)((const int *)(jb + o_ints) + 2 * ndp);
-                    double *jpart = (double *)(jb + o_part);
-                    {
-                        const int w = ((ent & 255) << 5) + lane;
-                        int p1 = 0, p2 = 0, nsub = 0, sub0 = 0;
-                        const bool rhs = w >= jnpad;
-                        int prt = 0;
-                        if (rhs) { // sample p1 against block points [sub0, sub0 + nsub)
-                            p1 = w - jnpad;
-                            if (nsplit > 1) {
-                                while (p1 >= jnapad) { p1 -= jnapad; prt++; } // uniform per round
-                                sub0 = (prt * P.ndb) / nsplit;
-                                nsub = ((prt + 1) * P.ndb) / nsplit - sub0;
-                            } else {
-                                nsub = P.ndb;
-                            }
-                            if (p1 >= jna) nsub = 0;
-                            p2 = ndp + sub0;
-                        } else if (w < jnpairs) {
-                            if (jfull) {
-                                const int rc = tri[w];
-                                p1 = rc & 255; p2 = (rc >> 8) + 1; nsub = 1; // p1 < p2
-                            } else {
-                                int a = (w * magic) >> 16, q = w - a * jna;
-                                if (q < 0) { a--; q += jna; }
-                                if (q >= jna) { a++; q -= jna; }
-                                const int p = jnewpos[a];
-                                p1 = p < q ? p : q; p2 = p < q ? q : p;
-                                nsub = p == q ? 0 : 1;
-                            }
-                        }
-                        const int p2first = p2;
-                        double acc = 0.0;
-                        for (int sub = sub0; sub < sub0 + nsub; sub++, p2++) {
-                            double h2v[K3D_MAXNST] = {0.0, 0.0, 0.0, 0.0};
-                            const double *u1 = jut + p1 * ustride, *u2 = jut + p2 * ustride;
-#pragma unroll
-                            for (int st = 0; st < K3D_MAXNST; st++) {
-                                if (st < P.nst) {
-                                    const double dx = u1[4 * st] - u2[4 * st],
-                                                 dy = u1[4 * st + 1] - u2[4 * st + 1],
-                                                 dz = u1[4 * st + 2] - u2[4 * st + 2];
-                                    h2v[st] = dx * dx + dy * dy + dz * dz;
-                                }
-                            }
-                            double c = cova_from_h2(P, Q, h2v, s_exptab);
-                            if (rhs && P.ndb > 1) { // krige3d.py:792-796
-                                const double dx = (jpx[p1] - s_jloc[jw][0]) - db[sub],
-                                             dy = (jpy[p1] - s_jloc[jw][1]) - db[P.ndb + sub],
-                                             dz = (jpz[p1] - s_jloc[jw][2]) - db[2 * P.ndb + sub];
-                                if (dx * dx + dy * dy + dz * dz < K3D_EPS) c -= P.c0;
-                            }
-                            acc += c;
-                        }
-                        if (rhs) {
-                            if (nsub) { // b row (krige3d.py:797-798)
-                                if (nsplit > 1)
-                                    jpart[prt * napad_max + p1] = acc;
-                                else
-                                    jPm[pk(jR - p1, 1)] = acc;
-                            }
-                        } else if (nsub) {
-                            jPm[pk(jR - p1, jR - p2first)] = acc;
+                    if constexpr (BLOCK) {
+                        if (rhs) { // krige3d.py:792-796: a block point on the sample loses the nugget
+                            const int sub = p2r - ndp + k;
+                            const double dx = relx - db[sub], dy = rely - db[P.ndb + sub],
+                                         dz = relz - db[2 * P.ndb + sub];
+                            if (dx * dx + dy * dy + dz * dz < K3D_EPS) c -= P.c0;
                         }
                     }
+                    acc += c;
                 }
-            }
+                if (BLOCK && rhs) // partial sum of the block average, added up by the owner
+                    sts_f64(jb + o_part + ((prt * napad_max + p1) << 3), acc);
+                else
+                    sts_f64(jb + (pk(jR - p1, rhs ? 1 : jR - p2r) << 3), acc);
             }
         }
         K3D_PHASE_BARRIER();
         if (solve) {
             if (na == 1) { // krige3d.py:423-468 (mdt == 0 here, R == 2)
                 double cb = Pm[pk(R, 1)];
-                if (nsplit > 1) {
+                if constexpr (BLOCK) {
                     cb = 0.0;
                     for (int q = 0; q < nsplit; q++) cb += part[q * napad_max];
                     cb /= (double)P.ndb;
@@ -1476,10 +1413,10 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         Pm[pk(R - pos, 0)] = va[pos];
                     }
                 }
-                if (nsplit > 1 || P.itrend || drift) {
+                if (BLOCK || P.itrend || drift) {
                     for (int i = lane; i < na; i += 32) {
                         const int ri = R - i;
-                        if (nsplit > 1) { // b row from the partial sums (krige3d.py:797-798)
+                        if constexpr (BLOCK) { // b row from the partial sums (krige3d.py:797-798)
                             double cb = 0.0;
                             for (int q = 0; q < nsplit; q++) cb += part[q * napad_max + i];
                             Pm[pk(ri, 1)] = cb / (double)P.ndb;
@@ -1657,8 +1594,8 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
     c->ndp = (p->ndmax + 3) & ~3;
     c->nst = p->nst;
     c->ndb = p->ndb;
-    c->ustride = 4 * p->nst;
     c->has_ext = (p->ktype == 2 || p->ktype == 3) ? 1 : 0;
+    c->need_xyz = (p->mdt > 1 || p->ndb > 1) ? 1 : 0;
     const int amax = amax_for(c->rtot);
     c->urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c->rtot;
     c->reuse = amax > 0 ? 1 : 0;
@@ -1672,7 +1609,12 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
     // with a full-cost node (no covariance reuse), so short walks hurt: score = warps per SM *
     // per / (per + 4) with per = nodes per warp and tile.  Registers cap an SM at 20 warps
     // (102 per thread; 24 warps of 85 for the small-system kernel, whose CTAs hold <= 8 warps).
-    const int max_cta_warps = amax == 5 ? 8 : 20, max_sm_warps = amax == 5 ? 24 : 20;
+#ifdef K3D_REG80
+    const bool small = amax == 5 || amax == 9;
+#else
+    const bool small = amax == 5;
+#endif
+    const int max_cta_warps = small ? 8 : 20, max_sm_warps = small ? 24 : 20;
     static const int shapes[][2] = {{2, 10}, {1, 20}, {1, 18}, {2, 8}, {1, 16}, {1, 14}, {2, 6},
                                     {1, 12}, {1, 10}, {2, 4}, {1, 8}, {1, 6}, {1, 4},
                                     {3, 8}, {3, 6}, {3, 5}, {4, 4}, {5, 3}, {8, 2}, {6, 2}, {4, 2},
@@ -1681,6 +1623,12 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
     BCfg pick = *c;
     int force_ctas = 0, force_warps = 0; // tuning knob: K3D_SOLVE_SHAPE="ctas,warps"
     if (const char *e = getenv("K3D_SOLVE_SHAPE")) sscanf(e, "%d,%d", &force_ctas, &force_warps);
+    // Record stride of the structure-space table: 4 doubles per structure, plus 2 when that
+    // costs no occupancy (point kriging) -- a stride of 2 mod 4 doubles spreads the 16-byte
+    // loads of 8 consecutive records over all banks (the kernel sits at 70 % of the
+    // shared-memory wavefront peak; the plain stride makes them 4-way conflicts).
+    for (int pad = p->ndb > 1 ? 0 : 2; pad >= 0; pad -= 2) {
+    c->ustride = 4 * p->nst + pad;
     for (unsigned i = 0; i < sizeof(shapes) / sizeof(shapes[0]); i++) {
         const int ctas = shapes[i][0], warps = shapes[i][1];
         if (warps > max_cta_warps || ctas * warps > max_sm_warps) continue;
@@ -1698,6 +1646,7 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
             c->smem_bytes = bytes;
             pick = *c;
         }
+    }
     }
     if (best <= 0.0) return K3D_ECAPACITY;
     *c = pick;

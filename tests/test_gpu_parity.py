@@ -192,6 +192,9 @@ def _edge_data(n, seed=11, ext=(12, 10, 6)):
     (dict(ikrige=1, idrift=[True, True, True] + [False] * 6, ndmax=12), 300),  # linear drift
     (dict(ikrige=1, itrend=True, idrift=[True] + [False] * 8, ndmax=12), 300),  # trend
     (dict(ikrige=0, nxdis=2, nydis=2, nzdis=2, ndmax=10), 200),                # block SK
+    (dict(ikrige=1, nxdis=3, nydis=1, nzdis=1, ndmax=10), 200),                # 3 block points
+    (dict(ikrige=1, nxdis=1, nydis=2, nzdis=1, ndmax=40), 300),                # 2 points, 2 groups
+    (dict(ikrige=1, nxdis=5, nydis=5, nzdis=4, ndmax=12), 200),                # 100 points
     (dict(ikrige=0, it=[3], c0=0.3, cc=[0.7]), 150),                           # gaussian
     (dict(ikrige=1, it=[4], c0=0.1, cc=[0.4], aa_hmax=[1.2], aa_hmin=[1.2], aa_vert=[1.2]), 150),
     (dict(ikrige=1, it=[5], c0=0.3, cc=[0.7]), 150),                           # hole effect
