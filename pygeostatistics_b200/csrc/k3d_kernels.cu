@@ -1627,7 +1627,10 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
     // costs no occupancy (point kriging) -- a stride of 2 mod 4 doubles spreads the 16-byte
     // loads of 8 consecutive records over all banks (the kernel sits at 70 % of the
     // shared-memory wavefront peak; the plain stride makes them 4-way conflicts).
-    for (int pad = p->ndb > 1 ? 0 : 2; pad >= 0; pad -= 2) {
+    int force_pad = -1; // tuning knob: K3D_FORCE_PAD=0|1
+    if (const char *e = getenv("K3D_FORCE_PAD")) force_pad = atoi(e);
+    for (int pad = 2; pad >= 0; pad -= 2) {
+    if (force_pad >= 0 ? (pad != 2 * force_pad) : (p->ndb > 1 && pad)) continue;
     c->ustride = 4 * p->nst + pad;
     for (unsigned i = 0; i < sizeof(shapes) / sizeof(shapes[0]); i++) {
         const int ctas = shapes[i][0], warps = shapes[i][1];
