@@ -276,7 +276,8 @@ def main():
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt[0]) * 1e3,
                "includes": "Krige3d(par, data).kt3d(): super-block set-up (binning, template "
                            "kernel), pinned H2D of samples/index, search + solve kernels, D2H of "
-                           "est/var/status" + ("; all-gather of slabs" if world > 1 else "")}
+                           "est/var/status" + ("; all-gather of slabs" if world > 1 else
+                                               " (overlapped with the kernels over runs of z-planes)")}
 
     if rank == 0:
         tfl = C_double()
