@@ -7,7 +7,8 @@
 //                       solve + estimate + variance      krige3d.py:590-614
 // The neighbour lists travel between them through global memory (HBM is not the bound:
 // 128 B per node against 6.5 TB/s), which lets the light search run at 32 warps per SM
-// and the register-heavy solve at up to 20.
+// and the register-heavy solve at up to 20.  The same kernels estimate at listed locations
+// (cross-validation / jackknife, krige3d.py:310-332, 359-363) when given a K3dPoints.
 //
 // Mapping to the machine (DESIGN.md has the full account):
 //   * one CTA per "tile" = the grid nodes that fall in one super block; all of them
@@ -18,6 +19,8 @@
 //     anisotropic distance under exact bounds inherited from the previous node, compact
 //     the hits with ballots and remove the surplus (octant rule, ndmax) by warp-wide
 //     lexicographic maxima;
+//   * the covariances the nodes in flight need are dealt out over the warps of the CTA in
+//     rounds of 32, evaluated from per-structure pre-scaled coordinates (no division);
 //   * the (n+mdt) system is assembled in shared memory in a mirrored packed-triangular
 //     layout -- re-using the sample-sample covariances of the previous node -- bordered by
 //     the right-hand side and the data vector, so that a single register-resident LDL^T
