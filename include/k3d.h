@@ -176,6 +176,10 @@ int k3d_build_template(int32_t nxsup, int32_t nysup, int32_t nzsup, double xsizs
 int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
                         const K3dOutputs *out);
 
+/* k3d_krige_points with HOST buffers (every pointer of `in`, `pts`, `out` is a host pointer). */
+int k3d_krige_points_host(const K3dParams *p, const K3dInputs *in, const K3dPoints *pts,
+                          const K3dOutputs *out);
+
 /* Kernel launch facts for the last k3d_krige_slab on this thread (bench / tests).
    `launches` counts kernels launched so far: a slab takes one search and one solve kernel
    per run of z-planes (one run unless the neighbour scratch would exceed 4 GB). */

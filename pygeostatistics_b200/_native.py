@@ -67,7 +67,7 @@ class K3dLaunchInfo(C.Structure):
 
 # every symbol include/k3d.h declares
 SYMBOLS = ("k3d_version", "k3d_last_error", "k3d_krige_slab", "k3d_krige_points",
-           "k3d_build_template", "k3d_krige_slab_host", "k3d_last_launch",
+           "k3d_build_template", "k3d_krige_slab_host", "k3d_krige_points_host", "k3d_last_launch",
            "k3d_measure_fp64_peak")
 
 _lib = None
@@ -90,6 +90,9 @@ def lib():
         L.k3d_krige_points.restype = C.c_int
         L.k3d_krige_points.argtypes = [C.POINTER(K3dParams), C.POINTER(K3dInputs),
                                        C.POINTER(K3dPoints), C.POINTER(K3dOutputs), C.c_void_p]
+        L.k3d_krige_points_host.restype = C.c_int
+        L.k3d_krige_points_host.argtypes = [C.POINTER(K3dParams), C.POINTER(K3dInputs),
+                                            C.POINTER(K3dPoints), C.POINTER(K3dOutputs)]
         L.k3d_krige_slab_host.restype = C.c_int
         L.k3d_krige_slab_host.argtypes = [C.POINTER(K3dParams), C.POINTER(K3dInputs), C.c_int32,
                                           C.c_int32, C.POINTER(K3dOutputs)]

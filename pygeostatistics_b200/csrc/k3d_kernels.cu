@@ -1934,15 +1934,22 @@ int k3d_measure_fp64_peak(double *tflops, double *ms, void *stream)
     return K3D_OK;
 }
 
-int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
-                        const K3dOutputs *out)
+// Host-buffer variant of both entry points: one device arena, copies in, the kernels,
+// copies out, one synchronisation.
+static int krige_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
+                      const K3dOutputs *out, const K3dPoints *pts)
 {
-    int rc = validate(p, in, iz0, iz1, out);
+    int rc = validate(p, in, iz0, iz1, out, pts != nullptr);
     if (rc) return rc;
+    if (pts && (pts->npts < 0 || pts->npts > 0x7fffffff)) return fail(K3D_EINVAL, "bad number of locations");
+    if (pts && pts->npts > 0 && (!pts->x || !pts->y || !pts->z || !pts->start))
+        return fail(K3D_EINVAL, "NULL location array");
     const size_t nd = (size_t)in->nd;
     const size_t nsb = (size_t)p->nxsup * p->nysup * p->nzsup;
-    const size_t nodes = (size_t)(iz1 - iz0) * p->nx * p->ny;
+    const size_t nodes = pts ? (size_t)pts->npts : (size_t)(iz1 - iz0) * p->nx * p->ny;
     const bool ext = (p->ktype == 2 || p->ktype == 3);
+    if (pts && ext && nodes > 0 && !pts->ext)
+        return fail(K3D_EINVAL, "ikrige 2/3 needs the external value of every location");
     cudaStream_t st = nullptr;
     CUDA_TRY(cudaStreamCreate(&st));
     // one device arena for everything
@@ -1952,6 +1959,8 @@ int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, in
     size_t o_sec = take(ext ? nd * 8 : 0), o_sb = take((nsb + 1) * 4), o_runs = take((size_t)in->nruns * 8);
     size_t o_nx = take((p->nxsup + 1) * 4), o_ny = take((p->nysup + 1) * 4), o_nz = take((p->nzsup + 1) * 4);
     size_t o_db = take((size_t)p->ndb * 24), o_ext = take(ext ? nodes * 8 : 0);
+    size_t o_px = take(pts ? nodes * 8 : 0), o_py = take(pts ? nodes * 8 : 0), o_pz = take(pts ? nodes * 8 : 0);
+    size_t o_ps = take(pts ? (nsb + 1) * 4 : 0);
     size_t o_est = take(nodes * 8), o_var = take(nodes * 8);
     size_t o_ni = take(out->nbr_idx ? nodes * p->ndmax * 4 : 0), o_nc = take(out->nbr_cnt ? nodes * 4 : 0);
     size_t o_st = take(out->status ? nodes : 0), o_ca = take(out->ncand ? nodes * 4 : 0);
@@ -1966,10 +1975,14 @@ int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, in
         cudaMemcpyAsync(d + (dst), (src), (bytes), cudaMemcpyHostToDevice, st) != cudaSuccess) \
         rc = fail(K3D_ECUDA, "host to device copy failed");
     H2D(o_sx, in->sx, nd * 8) H2D(o_sy, in->sy, nd * 8) H2D(o_sz, in->sz, nd * 8) H2D(o_sv, in->sv, nd * 8)
-    if (ext) { H2D(o_sec, in->ssec, nd * 8) H2D(o_ext, in->extgrid, nodes * 8) }
+    if (ext) { H2D(o_sec, in->ssec, nd * 8) H2D(o_ext, pts ? pts->ext : in->extgrid, nodes * 8) }
     H2D(o_sb, in->sbstart, (nsb + 1) * 4) H2D(o_runs, in->runs, (size_t)in->nruns * 8)
     H2D(o_nx, in->nodex0, (p->nxsup + 1) * 4) H2D(o_ny, in->nodey0, (p->nysup + 1) * 4)
     H2D(o_nz, in->nodez0, (p->nzsup + 1) * 4) H2D(o_db, in->dbxyz, (size_t)p->ndb * 24)
+    if (pts) {
+        H2D(o_px, pts->x, nodes * 8) H2D(o_py, pts->y, nodes * 8) H2D(o_pz, pts->z, nodes * 8)
+        H2D(o_ps, pts->start, (nsb + 1) * 4)
+    }
 #undef H2D
     if (rc == K3D_OK) {
         K3dInputs di = *in;
@@ -1977,14 +1990,22 @@ int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, in
         di.sv = (double *)(d + o_sv); di.ssec = ext ? (double *)(d + o_sec) : nullptr;
         di.sbstart = (int32_t *)(d + o_sb); di.runs = (int16_t *)(d + o_runs);
         di.nodex0 = (int32_t *)(d + o_nx); di.nodey0 = (int32_t *)(d + o_ny); di.nodez0 = (int32_t *)(d + o_nz);
-        di.dbxyz = (double *)(d + o_db); di.extgrid = ext ? (double *)(d + o_ext) : nullptr;
+        di.dbxyz = (double *)(d + o_db); di.extgrid = (ext && !pts) ? (double *)(d + o_ext) : nullptr;
         K3dOutputs dout;
         dout.est = (double *)(d + o_est); dout.var = (double *)(d + o_var);
         dout.nbr_idx = out->nbr_idx ? (int32_t *)(d + o_ni) : nullptr;
         dout.nbr_cnt = out->nbr_cnt ? (int32_t *)(d + o_nc) : nullptr;
         dout.status = out->status ? (uint8_t *)(d + o_st) : nullptr;
         dout.ncand = out->ncand ? (int32_t *)(d + o_ca) : nullptr;
-        rc = k3d_krige_slab(p, &di, iz0, iz1, &dout, st);
+        if (pts) {
+            K3dPoints dp = *pts;
+            dp.x = (double *)(d + o_px); dp.y = (double *)(d + o_py); dp.z = (double *)(d + o_pz);
+            dp.ext = ext ? (double *)(d + o_ext) : nullptr;
+            dp.start = (int32_t *)(d + o_ps);
+            rc = k3d_krige_points(p, &di, &dp, &dout, st);
+        } else {
+            rc = k3d_krige_slab(p, &di, iz0, iz1, &dout, st);
+        }
     }
 #define D2H(dst, src, bytes)                                                              \
     if (rc == K3D_OK && (dst) && (bytes) > 0 &&                                           \
@@ -1999,6 +2020,19 @@ int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, in
     cudaFree(d);
     cudaStreamDestroy(st);
     return rc;
+}
+
+int k3d_krige_slab_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
+                        const K3dOutputs *out)
+{
+    return krige_host(p, in, iz0, iz1, out, nullptr);
+}
+
+int k3d_krige_points_host(const K3dParams *p, const K3dInputs *in, const K3dPoints *pts,
+                          const K3dOutputs *out)
+{
+    if (!pts) return fail(K3D_EINVAL, "NULL argument");
+    return krige_host(p, in, 0, p ? p->nz : 0, out, pts);
 }
 
 } // extern "C"

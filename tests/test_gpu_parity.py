@@ -313,6 +313,29 @@ def test_host_buffer_c_abi_entry():
     # be ordered differently (covariance reuse); the values agree to rounding
     assert np.allclose(est, k.estimation, rtol=1e-11, atol=1e-12, equal_nan=True)
     assert np.allclose(var, k.estimation_variance, rtol=1e-11, atol=1e-12, equal_nan=True)
+    # k3d_krige_points_host: cross-validation of the same data through host pointers
+    kx = Krige3d(dict(par, option=1), data=data)
+    kx.verbose = False
+    kx.kt3d()
+    x, y, z = (np.ascontiguousarray(data[c]) for c in 'xyz')
+    blk = s.block_of_locations(x, y, z)
+    order = np.argsort(blk, kind='stable')
+    nsup = s.nxsup * s.nysup * s.nzsup
+    pa = dict(x=x[order], y=y[order], z=z[order],
+              start=np.concatenate([[0], np.cumsum(np.bincount(blk, minlength=nsup))]).astype(np.int32))
+    Q = _native.K3dPoints()
+    Q.npts = len(x)
+    for name in ('x', 'y', 'z', 'start'):
+        setattr(Q, name, pa[name].ctypes.data)
+    Q.exclude_coincident = 1
+    pe = np.empty(len(x)); pv = np.empty(len(x))
+    O = _native.K3dOutputs()
+    O.est, O.var = pe.ctypes.data, pv.ctypes.data
+    _native.check(_native.lib().k3d_krige_points_host(C.byref(P), C.byref(I), C.byref(Q), C.byref(O)))
+    back = np.empty(len(x)); back[order] = pe
+    assert np.array_equal(back, kx.estimation, equal_nan=True)
+    back[order] = pv
+    assert np.array_equal(back, kx.estimation_variance, equal_nan=True)
 
 
 # ---------------------------------------------------------------- option 1 / 2: listed locations
