@@ -37,6 +37,26 @@ WORKLOADS = {
 }
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version
+    banner under torchrun goes through printf), so the process's fd 1 is pointed at stderr
+    and the result line is written to a private duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def algorithmic_flops(par, nbar, cbar, mdt):
     """flops per node with n = mean neighbours used, C = mean
     candidates distance-tested (add/mul = 1, FMA = 2, div/sqrt/exp/pow/cos = 1 each)."""
@@ -140,7 +160,7 @@ def run_reference(args):
     dt = time.time() - t0
     value = len(nodes) * args.steps / dt
     sample = "%d consecutive nodes from the central z-plane per step" % len(nodes)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -151,7 +171,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is pure Python+Numba (808 nodes/s on config 1 in the build container, "
                 "SURVEY.md section 6); this arm times its compiled C restatement (oracle/) "
-                "with OpenMP on all host cores"}))
+                "with OpenMP on all host cores"})
 
 
 def main():
@@ -165,6 +185,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -179,8 +200,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries the one JSON line: NCCL's own banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     par, data, sec = k3d_configs.config(args.config, args.scale)
@@ -332,7 +351,7 @@ def main():
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
             _, line["cpu_baseline"] = cpu_baseline(par, data, sec)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
