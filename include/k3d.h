@@ -39,6 +39,14 @@ enum {
     K3D_ECAPACITY = -4    /* configuration does not fit the kernel's shared memory */
 };
 
+/* K3dParams.flags */
+enum {
+    /* kb2d's rule for a single neighbour under ordinary kriging (krige2d.py:360-363):
+       estimate = the datum, variance = cbb - 2 cb + cov(0); krige3d rejects the node
+       (krige3d.py:383) */
+    K3D_FLAG_OK_ONE_SAMPLE = 1
+};
+
 /* per-node status codes written to K3dOutputs.status (krige3d.py:377-389, 590-596) */
 enum {
     K3D_ST_OK = 0,
@@ -61,7 +69,7 @@ typedef struct K3dParams {
     double xsiz, ysiz, zsiz;
     /* search (krige3d.py:99-111, 192) */
     int32_t ndmin, ndmax, noct;
-    int32_t _pad1;
+    int32_t flags;          /* K3D_FLAG_* (0 for krige3d) */
     double radsqd;
     /* kriging type (krige3d.py:113-119): 0 SK, 1 OK/UK, 2 non-stationary SK, 3 KED */
     int32_t ktype;

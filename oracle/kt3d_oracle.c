@@ -63,6 +63,8 @@ typedef struct {
     int32_t nxsup, nysup, nzsup;
     /* block discretisation (joint list of ndb points, repair D9) */
     int32_t ndb;
+    /* bit 0: kb2d's one-sample rule under ordinary kriging (krige2d.py:360-363) */
+    int32_t flags;
 } OrcParams;
 
 /* super_block.py:349-378 and krige3d.py:803-836 (identical bodies) */
@@ -396,7 +398,7 @@ static void orc_location(const OrcParams *p, double xloc, double yloc, double zl
             nbr_idx[i] = (int32_t)cand[i].i;
     if (na < p->ndmin) /* krige3d.py:377 */
         goto done;
-    if (na >= 1 && na <= mdt) /* krige3d.py:383 */
+    if (na >= 1 && na <= mdt && !(na == 1 && mdt == 1 && (p->flags & 1))) /* krige3d.py:383 */
         goto done;
     if (na == 0) /* repair D15 */
         goto done;
@@ -420,6 +422,10 @@ static void orc_location(const OrcParams *p, double xloc, double yloc, double zl
         double s = cb / p->cbb;
         est = s * vra[0] + (1 - s) * skmean;
         estv = p->cbb - s * cb;
+        if (mdt == 1) { /* krige2d.py:360-363 (flag bit 0) */
+            est = vra[0];
+            estv = p->cbb - 2.0 * cb + p->maxcov;
+        }
         goto done;
     }
 

@@ -44,7 +44,7 @@ class OrcParams(C.Structure):
         ("maxcov", C.c_double), ("resc", C.c_double), ("unbias", C.c_double),
         ("cbb", C.c_double), ("bv", C.c_double * MAXDRIFT),
         ("nxsup", C.c_int32), ("nysup", C.c_int32), ("nzsup", C.c_int32),
-        ("ndb", C.c_int32),
+        ("ndb", C.c_int32), ("flags", C.c_int32),
     ]
 
 
@@ -153,6 +153,8 @@ def prepare(par, cols, prop_names):
                             np.append(par['ang2'], par['sang2']),
                             np.append(par['ang3'], par['sang3']),
                             np.append(anis1, sanis1), np.append(anis2, sanis2))
+    if par.get('_search_identity'):   # krige2d front end: plain dx^2 + dy^2 search distance
+        rot[-1] = np.eye(3)
     maxcov = par['c0']
     for i in range(nst):
         maxcov += 999 if par['it'][i] == 4 else par['cc'][i]
@@ -237,6 +239,7 @@ def prepare(par, cols, prop_names):
         P.bv[i] = bv[i]
     P.nxsup, P.nysup, P.nzsup = nxsup, nysup, nzsup
     P.ndb = ndb
+    P.flags = int(par.get('_flags', 0))
     L.orc_block_covariance.argtypes = [C.POINTER(OrcParams)] + [C.POINTER(C.c_double)] * 3
     P.cbb = maxcov
     P.cbb = L.orc_block_covariance(C.byref(P), _p(xdb, C.c_double), _p(ydb, C.c_double),

@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("K3D_LIB", os.path.join(HERE, "csrc", "libk3d.so"))
 
 MAXNST, MAXDRIFT, MAXNDMAX, MAXDIS = 4, 9, 64, 128
+FLAG_OK_ONE_SAMPLE = 1
 
 
 class K3dError(RuntimeError):
@@ -21,7 +22,7 @@ class K3dParams(C.Structure):
         ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("_pad0", C.c_int32),
         ("xmn", C.c_double), ("ymn", C.c_double), ("zmn", C.c_double),
         ("xsiz", C.c_double), ("ysiz", C.c_double), ("zsiz", C.c_double),
-        ("ndmin", C.c_int32), ("ndmax", C.c_int32), ("noct", C.c_int32), ("_pad1", C.c_int32),
+        ("ndmin", C.c_int32), ("ndmax", C.c_int32), ("noct", C.c_int32), ("flags", C.c_int32),
         ("radsqd", C.c_double),
         ("ktype", C.c_int32), ("itrend", C.c_int32), ("idrift", C.c_int32 * MAXDRIFT),
         ("mdt", C.c_int32),

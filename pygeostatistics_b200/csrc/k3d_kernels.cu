@@ -1177,8 +1177,8 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         } else if (na < P.ndmin || na == 0) { // krige3d.py:377, repair D15
             status = K3D_ST_NOT_ENOUGH_DATA;
             nprev = -1;
-        } else if (na <= mdt) { // krige3d.py:383
-            status = K3D_ST_NOT_ENOUGH_DRIFT;
+        } else if (na <= mdt && !(na == 1 && mdt == 1 && (P.flags & K3D_FLAG_OK_ONE_SAMPLE))) {
+            status = K3D_ST_NOT_ENOUGH_DRIFT; // krige3d.py:383
             nprev = -1;
         } else {
             solve = true;
@@ -1379,6 +1379,10 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 const double v0 = in.sv[pid[0]];
                 est = sw * v0 + (1.0 - sw) * skmean;
                 var = P.cbb - sw * cb;
+                if (mdt == 1) { // kb2d's ordinary-kriging rule, krige2d.py:360-363
+                    est = v0;
+                    var = P.cbb - 2.0 * cb + P.maxcov;
+                }
                 nprev = -1;
             } else {
                 // Border of the system (krige3d.py:764-767, 493-583 with repair D6).  What

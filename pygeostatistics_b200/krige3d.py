@@ -137,6 +137,8 @@ class Krige3d(object):
         self.verbose = True
         self.timings = {}
         self._dev = None
+        self.search_identity = False   # Krige2d: isotropic search with the exact identity matrix
+        self.flags = 0                 # K3dParams.flags (include/k3d.h)
 
     # ------------------------------------------------------------------ parameters
     def _read_params(self):
@@ -254,6 +256,8 @@ class Krige3d(object):
         rot[:, 2, 0] = afac2 * (sint * sina + cost * sinb * cosa)
         rot[:, 2, 1] = afac2 * (-sint * cosa + cost * sinb * sina)
         rot[:, 2, 2] = afac2 * (cost * cosb)
+        if self.search_identity:  # krige2d front end: plain dx*dx + dy*dy (krige2d.py:318-320)
+            rot[-1] = np.eye(3)
         self.rotmat = rot
 
     def _max_covariance(self):
@@ -367,6 +371,7 @@ class Krige3d(object):
         P.xmn, P.ymn, P.zmn = self.xmn, self.ymn, self.zmn
         P.xsiz, P.ysiz, P.zsiz = self.xsiz, self.ysiz, self.zsiz
         P.ndmin, P.ndmax, P.noct = self.ndmin, self.ndmax, self.noct
+        P.flags = int(self.flags)
         P.radsqd = self.radsqd
         P.ktype, P.itrend = self.ktype, int(bool(self.itrend))
         P.mdt = self.mdt

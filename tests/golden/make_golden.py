@@ -28,6 +28,13 @@ Three fixture families are written (all small, all committed):
                          SURVEY.md section 0, fact 4): SK and OK, nested and
                          anisotropic variograms, rotated anisotropic search.
 
+  krige2d_reference.npz  the unmodified Krige2d(par).kd2d() (krige2d.py) on the shipped
+                         testData/test_krige2d.par as shipped (SK) and with isk=1 (OK), and
+                         on synthetic cases (nested anisotropic variogram, Gaussian-free,
+                         SK and OK, single-neighbour nodes, ndmin) in which never more than
+                         `ndmax` samples are in range, so that its order-dependent
+                         neighbour rule (defect K1) cannot fire.
+
 Nothing here is imported by the product; the GPU box never needs /root/reference.
 """
 import io
@@ -360,10 +367,73 @@ def golden_small(k3):
             int(np.isnan(k.estimation).sum())))
 
 
+def golden_krige2d():
+    """Unmodified pygeostatistics/krige2d.py on cases its defects do not touch."""
+    import pygeostatistics.krige2d as k2
+    out = {}
+    base = json.load(open(os.path.join(REF, "testData", "test_krige2d.par")))
+
+    def run(par, cols):
+        with tempfile.TemporaryDirectory() as wd:
+            data = os.path.join(wd, "d.gslib")
+            names = list(cols.keys())
+            with open(data, "w") as f:
+                f.write("golden\n%d\n%s\n" % (len(names), "\n".join(names)))
+                for row in zip(*[cols[n] for n in names]):
+                    f.write("\t".join(repr(float(c)) for c in row) + "\n")
+            par = dict(par, datafl=data)
+            pf = os.path.join(wd, "p.par")
+            json.dump(par, open(pf, "w"))
+            k = k2.Krige2d(pf)
+            k.read_data()
+            # defect K1 must not fire: never more than ndmax samples in range
+            gx = par['xmn'] + np.arange(par['nx']) * par['xsiz']
+            gy = par['ymn'] + np.arange(par['ny']) * par['ysiz']
+            d2 = (cols['x'][None, None, :] - gx[:, None, None]) ** 2 + \
+                 (cols['y'][None, None, :] - gy[None, :, None]) ** 2
+            nin = (d2 <= par['radius'] ** 2).sum(axis=2)
+            assert nin.max() <= par['ndmax'], (nin.max(), par['ndmax'])
+            with contextlib.redirect_stdout(io.StringIO()):
+                k.kd2d()
+            return k, nin
+
+    # shipped case, SK and OK
+    ref = np.loadtxt(os.path.join(REF, "testData", "test.gslib"), skiprows=5)
+    cols = {'x': ref[:, 0], 'y': ref[:, 1], 'por': ref[:, 2]}
+    for tag, isk in (("sk", 0), ("ok", 1)):
+        k, nin = run(dict(base, isk=isk), cols)
+        out["c1_est_" + tag], out["c1_var_" + tag] = k.estimation, k.estimation_variance
+        print("krige2d c1 %s: in range %d..%d, NaN %d" % (tag, nin.min(), nin.max(),
+                                                          int(np.isnan(k.estimation).sum())))
+    out["c1_par"] = np.array([json.dumps(base)])
+    out["c1_xyv"] = np.stack([cols['x'], cols['y'], cols['por']])
+    # synthetic: nested anisotropic exp + sph, OK, sparse data (nodes with 0 and 1 neighbours)
+    rng = np.random.default_rng(21)
+    n = 70
+    cols = {'x': rng.uniform(0, 40, n), 'y': rng.uniform(0, 30, n), 'v': rng.normal(size=n)}
+    syn = dict(base, nx=40, xmn=0.5, xsiz=1.0, ny=30, ymn=0.5, ysiz=1.0, nxdis=1, nydis=1,
+               ndmin=1, ndmax=24, radius=6.0, isk=1, skmean=0.1, nst=2, c0=0.1, it=[2, 1],
+               cc=[0.4, 0.5], azm=[30.0, 110.0], a_max=[12.0, 20.0], a_min=[5.0, 9.0])
+    # (block kriging cannot be pinned: `block_kriging` is only ever set to False,
+    #  krige2d.py:200-204, so any nxdis*nydis > 1 dies with AttributeError -- defect K5)
+    for tag, upd in (("ok_nested", {}), ("sk_nested", dict(isk=0, radius=7.5, ndmax=40)),
+                     ("ok_ndmin3", dict(ndmin=3))):
+        par = dict(syn, **upd)
+        k, nin = run(par, cols)
+        out["syn_%s_est" % tag], out["syn_%s_var" % tag] = k.estimation, k.estimation_variance
+        out["syn_%s_par" % tag] = np.array([json.dumps(par)])
+        print("krige2d %s: in range %d..%d, one-sample nodes %d, NaN %d" % (
+            tag, nin.min(), nin.max(), int((nin == 1).sum()), int(np.isnan(k.estimation).sum())))
+    out["syn_xyv"] = np.stack([cols['x'], cols['y'], cols['v']])
+    np.savez_compressed(os.path.join(HERE, "krige2d_reference.npz"), **out)
+
+
 if __name__ == "__main__":
     import warnings
     warnings.simplefilter("ignore")
     k3, sb = import_reference()
-    golden_c1(k3)
-    golden_kernels(k3, sb)
-    golden_small(k3)
+    if "--krige2d-only" not in sys.argv:
+        golden_c1(k3)
+        golden_kernels(k3, sb)
+        golden_small(k3)
+    golden_krige2d()

@@ -454,3 +454,67 @@ def test_cross_validation_ked_external_drift():
     names = [n for n in data if n not in ('x', 'y', 'z')]
     st, ores = _oracle_points(par, data, data['x'], data['y'], data['z'], ext=data[names[1]], koption=1)
     assert _compare_points(k, st, ores, vmax=float(np.max(np.abs(data[names[0]])))) > 0.5 * len(data['x'])
+
+
+# ---------------------------------------------------------------- krige2d front end
+def _write_geoeas(path, cols):
+    names = list(cols.keys())
+    with open(path, "w") as f:
+        f.write("data\n%d\n%s\n" % (len(names), "\n".join(names)))
+        for row in zip(*[cols[n] for n in names]):
+            f.write("  ".join(repr(float(c)) for c in row) + "\n")
+
+
+def test_krige2d_front_end_against_unmodified_reference(golden_dir, tmp_path):
+    """Krige2d(par).read_data()/kd2d() -- the reference's krige2d.py interface on the krige3d
+    kernels -- against runs of the unmodified reference (tests/golden/krige2d_reference.npz)."""
+    from pygeostatistics_b200.krige2d import Krige2d
+    from k2d_cases import krige2d_cases as _krige2d_cases
+    for tag, par, cols, est, var in _krige2d_cases(golden_dir):
+        data = tmp_path / (tag + ".gslib")
+        _write_geoeas(data, cols)
+        pf = tmp_path / (tag + ".par")
+        json.dump(dict(par, datafl=str(data)), open(pf, "w"))
+        k = Krige2d(str(pf))
+        k.verbose = False
+        k.read_data()
+        k.kd2d()
+        assert k.estimation.shape == (par['nx'], par['ny'])
+        assert np.array_equal(np.isnan(k.estimation), np.isnan(est)), tag
+        ok = ~np.isnan(est)
+        rel = np.abs(k.estimation[ok] - est[ok]) / np.maximum(np.abs(est[ok]), 1e-3)
+        assert rel.max() < EST_RTOL, (tag, rel.max())
+        assert np.max(np.abs(k.estimation_variance[ok] - var[ok])) < 1e-10, tag
+
+
+@pytest.mark.parametrize("upd", [dict(), dict(isk=0, nxdis=3, nydis=2), dict(it=[3, 1], ndmax=12)])
+def test_krige2d_dense_cases_against_oracle(upd, tmp_path):
+    """More than ndmax samples in range (the reference's neighbour rule is order dependent
+    there, defect K1: the ndmax nearest are kept), block kriging (crashes in the reference,
+    K5) and a Gaussian structure (K2): the repaired restatement is the oracle."""
+    from pygeostatistics_b200.krige2d import Krige2d
+    rng = np.random.default_rng(9)
+    n = 1500
+    cols = {'x': rng.uniform(0, 60, n), 'y': rng.uniform(0, 45, n), 'v': rng.normal(size=n)}
+    par = dict(datafl="", icolx=0, icoly=1, icolvr=2, tmin=-1e21, tmax=1e21, idbg=0,
+               dbgfl="kb2d.dbg", outfl="out.dat", nx=60, xmn=0.5, xsiz=1.0, ny=45, ymn=0.5,
+               ysiz=1.0, nxdis=1, nydis=1, ndmin=1, ndmax=16, radius=6.0, isk=1, skmean=0.0,
+               nst=2, c0=0.1, it=[2, 1], cc=[0.4, 0.5], azm=[30.0, 110.0], a_max=[12.0, 20.0],
+               a_min=[5.0, 9.0])
+    par.update(upd)
+    data = tmp_path / "d.gslib"
+    _write_geoeas(data, cols)
+    par['datafl'] = str(data)
+    k = Krige2d(par)
+    k.verbose = False
+    k.kd2d()
+    c3 = {'x': k.vr['x'], 'y': k.vr['y'], 'z': k.vr['z'], 'v': k.vr['v']}
+    st = orc.prepare(k.krige3d_params(), c3, ['v'])
+    e, v, _, cnt = orc.run(st, threads=8)
+    assert cnt.max() == par['ndmax']
+    e = e.reshape(par['ny'], par['nx']).T
+    v = v.reshape(par['ny'], par['nx']).T
+    assert np.array_equal(np.isnan(k.estimation), np.isnan(e))
+    ok = ~np.isnan(e)
+    assert np.all(np.abs(k.estimation[ok] - e[ok]) <= EST_RTOL * np.abs(e[ok]) + 1e-11)
+    assert np.all(np.abs(k.estimation_variance[ok] - v[ok]) <= VAR_RTOL * np.abs(v[ok]) + 1e-11)

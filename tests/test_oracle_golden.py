@@ -184,3 +184,27 @@ def test_oracle_locations_mode_properties():
     assert not (n1 == srt[:, None]).any()        # never its own neighbour
     assert np.nanmin(v1) > 1e-3 and np.nanmax(np.abs(e1 - v)) > 1e-2
     assert np.all(c1 <= par['ndmax'])
+
+
+from k2d_cases import krige2d_cases as _krige2d_cases  # noqa: E402
+
+
+def test_oracle_drives_krige2d_against_unmodified_reference(golden_dir):
+    """The krige2d front end maps onto the krige3d path (pygeostatistics_b200/krige2d.py):
+    the oracle, driven with that mapping, reproduces the unmodified reference krige2d.py
+    (nested anisotropic variograms, SK / OK, ndmin, nodes with a single neighbour: kb2d's
+    ordinary-kriging rule) wherever its order-dependent neighbour rule cannot fire."""
+    from pygeostatistics_b200.krige2d import Krige2d
+    for tag, par, cols, est, var in _krige2d_cases(golden_dir):
+        k = Krige2d(par)
+        p3 = k.krige3d_params()
+        cols = dict(cols, z=np.zeros_like(cols['x']))
+        names = [n for n in cols if n not in ('x', 'y', 'z')]
+        st = orc.prepare(p3, cols, names)
+        e, v, _, _ = orc.run(st, threads=4)
+        e = e.reshape(par['ny'], par['nx']).T
+        v = v.reshape(par['ny'], par['nx']).T
+        assert np.array_equal(np.isnan(e), np.isnan(est)), tag
+        ok = ~np.isnan(est)
+        assert np.max(np.abs(e[ok] - est[ok]) / np.maximum(np.abs(est[ok]), 1e-3)) < 1e-9, tag
+        assert np.max(np.abs(v[ok] - var[ok])) < 1e-10, tag
