@@ -17,6 +17,8 @@ unmodified reference on runs in which the defects do not fire, tests/golden/make
   K2  krige2d.py:143-145  the Gaussian term multiplies by the whole `cc` list.  Here `cc[iss]`.
   K3  krige2d.py:350-356  block kriging with one sample overwrites instead of summing the
       block-point covariances.  Here: their mean, as in `_many_sample`.
+  K5  krige2d.py:200-204  `block_kriging` is only ever set to False: any nxdis*nydis > 1 dies
+      with AttributeError.  Here block kriging works (the krige3d block average).
   K4  power structures (`it` 4) use PMX = 9999 both as the sill and inside the model
       (krige2d.py:117, 147); krige3d's convention differs (999, `maxcov - cc*h^a`) and the
       shared kernel follows krige3d: `it` 4 raises NotImplementedError here.
