@@ -1061,14 +1061,10 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
 // SOLVE kernel: kriging system assembly (krige3d.py:470-583, 748-801, 838-875), solve and
 // estimate (krige3d.py:590-614) from the neighbour lists of the search kernel
 // ---------------------------------------------------------------------------
-// BLOCK: block kriging (ndb > 1), whose right-hand side averages over the block points;
-// point kriging takes a leaner covariance loop driven by per-warp work-item lists.
+// BLOCK: block kriging (ndb > 1), whose right-hand side averages over the block points
+// (one round per part of the discretisation, partial sums added up by the owner warp).
 template <int AMAX, bool BLOCK>
-#ifdef K3D_REG80
-__global__ void __launch_bounds__(AMAX == 5 || AMAX == 9 ? 256 : 640, AMAX == 5 || AMAX == 9 ? K3D_SMALL_CTAS : 1)
-#else
 __global__ void __launch_bounds__(AMAX == 5 ? 256 : 640, AMAX == 5 ? K3D_SMALL_CTAS : 1)
-#endif
 k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
                  const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
                  const int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
@@ -1616,11 +1612,7 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
     // with a full-cost node (no covariance reuse), so short walks hurt: score = warps per SM *
     // per / (per + 4) with per = nodes per warp and tile.  Registers cap an SM at 20 warps
     // (102 per thread; 24 warps of 85 for the small-system kernel, whose CTAs hold <= 8 warps).
-#ifdef K3D_REG80
-    const bool small = amax == 5 || amax == 9;
-#else
     const bool small = amax == 5;
-#endif
     const int max_cta_warps = small ? 8 : 20, max_sm_warps = small ? 24 : 20;
     static const int shapes[][2] = {{2, 10}, {1, 20}, {1, 18}, {2, 8}, {1, 16}, {1, 14}, {2, 6},
                                     {1, 12}, {1, 10}, {2, 4}, {1, 8}, {1, 6}, {1, 4},
