@@ -425,6 +425,36 @@ def golden_krige2d():
         print("krige2d %s: in range %d..%d, one-sample nodes %d, NaN %d" % (
             tag, nin.min(), nin.max(), int((nin == 1).sum()), int(np.isnan(k.estimation).sum())))
     out["syn_xyv"] = np.stack([cols['x'], cols['y'], cols['v']])
+    # eight small random parameter sets (model types 1-2, one or two structures, any azimuth
+    # and anisotropy, SK / OK, off-origin non-unit grids)
+    nrand = 8
+    for i in range(nrand):
+        r = np.random.default_rng(100 + i)
+        nst = int(r.integers(1, 3))
+        nx, ny = int(r.integers(12, 22)), int(r.integers(10, 18))
+        xsiz, ysiz = float(r.choice([0.5, 1.0, 2.5])), float(r.choice([0.5, 1.0, 2.0]))
+        xmn, ymn = float(r.uniform(-50, 50)), float(r.uniform(-50, 50))
+        n = int(r.integers(25, 60))
+        cols = {'x': r.uniform(xmn - 0.5 * xsiz, xmn + (nx - 0.5) * xsiz, n),
+                'y': r.uniform(ymn - 0.5 * ysiz, ymn + (ny - 0.5) * ysiz, n),
+                'v': r.normal(size=n) * 3.0 + 10.0}
+        a_max = [float(v) for v in r.uniform(3.0, 15.0, nst) * max(xsiz, ysiz)]
+        par = dict(base, nx=nx, xmn=xmn, xsiz=xsiz, ny=ny, ymn=ymn, ysiz=ysiz, nxdis=1, nydis=1,
+                   ndmin=int(r.integers(1, 3)), ndmax=64,
+                   radius=float(r.uniform(2.5, 6.0) * max(xsiz, ysiz)),
+                   isk=int(r.integers(0, 2)), skmean=10.0, nst=nst, c0=float(r.uniform(0, 0.3)),
+                   it=[int(v) for v in r.integers(1, 3, nst)],
+                   cc=[float(v) for v in r.uniform(0.2, 1.0, nst)],
+                   azm=[float(v) for v in r.uniform(-90, 270, nst)], a_max=a_max,
+                   a_min=[float(a * v) for a, v in zip(a_max, r.uniform(0.3, 1.0, nst))])
+        k, nin = run(par, cols)
+        out["rand%d_est" % i], out["rand%d_var" % i] = k.estimation, k.estimation_variance
+        out["rand%d_par" % i] = np.array([json.dumps(par)])
+        out["rand%d_xyv" % i] = np.stack([cols['x'], cols['y'], cols['v']])
+        print("krige2d rand%d: isk %d nst %d it %s in range %d..%d, NaN %d" % (
+            i, par['isk'], nst, par['it'], nin.min(), nin.max(),
+            int(np.isnan(k.estimation).sum())))
+    out["nrand"] = np.array([nrand])
     np.savez_compressed(os.path.join(HERE, "krige2d_reference.npz"), **out)
 
 

@@ -18,3 +18,7 @@ def krige2d_cases(golden_dir):
     for tag in ("ok_nested", "sk_nested", "ok_ndmin3"):
         yield tag, json.loads(str(g['syn_%s_par' % tag][0])), {'x': x, 'y': y, 'v': v}, \
             g['syn_%s_est' % tag], g['syn_%s_var' % tag]
+    for i in range(int(g['nrand'][0])):
+        x, y, v = g['rand%d_xyv' % i]
+        yield "rand%d" % i, json.loads(str(g['rand%d_par' % i][0])), {'x': x, 'y': y, 'v': v}, \
+            g['rand%d_est' % i], g['rand%d_var' % i]
