@@ -292,3 +292,45 @@ def test_block_of_locations_equals_oracle_getindx():
     sb = orc.super_block_of(st, px, py, pz)
     flat = sb[:, 0] + sb[:, 1] * s.nxsup + sb[:, 2] * s.nxsup * s.nysup
     assert np.array_equal(s.block_of_locations(px, py, pz), flat)
+
+
+def test_krige2d_front_end_host_side(tmp_path):
+    """Krige2d (krige2d.py:19-104 interface): parameter file, checks, whitespace-separated
+    reader, and the krige3d mapping it runs with -- no GPU needed up to the launch."""
+    from pygeostatistics_b200 import Krige2d, _native
+    ref = os.path.join(ROOT, "tests", "golden", "krige2d_reference.npz")
+    g = np.load(ref)
+    par = json.loads(str(g['c1_par'][0]))
+    x, y, v = g['c1_xyv']
+    data = tmp_path / "d.gslib"
+    with open(data, "w") as f:
+        f.write("test\n3\nx\ny\npor\n")
+        for r in zip(x, y, v):
+            f.write("   ".join(repr(float(c)) for c in r) + "\n")
+    pf = tmp_path / "k2d.par"
+    json.dump(dict(par, datafl=str(data)), open(pf, "w"))
+    k = Krige2d(str(pf))
+    k.read_data()
+    assert k._2d and k.property_name == ['por'] and k.vr.dtype.names == ('x', 'y', 'por', 'z')
+    assert np.array_equal(k.vr['x'], x) and np.array_equal(k.vr['por'], v)
+    p3 = k.krige3d_params()
+    assert (p3['nz'], p3['noct'], p3['ikrige'], p3['radius_hmax']) == (1, 0, par['isk'], float(par['radius']))
+    assert p3['ang1'] == [float(a) for a in par['azm']] and p3['aa_hmin'] == [float(a) for a in par['a_min']]
+    assert p3['_search_identity'] and p3['_flags'] == _native.FLAG_OK_ONE_SAMPLE
+    for bad, exc in ((dict(it=[7]), ValueError), (dict(it=[5]), ValueError),
+                     (dict(it=[4], a_max=[1.5]), NotImplementedError),
+                     (dict(it=[4], a_max=[2.5]), ValueError), (dict(isk=2), ValueError),
+                     (dict(ndmax=65), ValueError)):
+        with pytest.raises(exc):
+            Krige2d(dict(par, **bad))
+    missing = dict(par)
+    del missing['radius']
+    with pytest.raises(KeyError):
+        Krige2d(missing)
+    # the krige3d class honours the two front-end switches
+    k3 = Krige3d({a: b for a, b in p3.items() if not a.startswith('_')},
+                 data={'x': x, 'y': y, 'z': np.zeros_like(x), 'por': v})
+    k3.search_identity = True
+    k3._preprocess(); k3._set_rotation()
+    assert np.array_equal(k3.rotmat[-1], np.eye(3))
+    assert k3.mdt == par['isk']
