@@ -202,6 +202,21 @@ typedef struct K3dLaunchInfo {
 } K3dLaunchInfo;
 int k3d_last_launch(K3dLaunchInfo *info);
 
+/* Gives back what the library holds between calls on behalf of the calling thread and
+   process: the per-thread timing events of k3d_last_launch and the unused memory of the
+   per-device scratch pools the neighbour lists travel through (up to ~4 GB per device,
+   kept between calls because re-allocating it costs more than the search kernel).
+   Safe to call at any time between runs; the next call re-creates what it needs. */
+int k3d_release(void);
+
+/* Self test of the in-line device math the covariance and the elimination use in place of
+   the CUDA library (exp for arguments <= 0, sqrt, reciprocal; the reference calls libm
+   through Numba, krige3d.py:838-875): evaluates `n` pseudo-random points per function on
+   the device and returns the largest distance, in units in the last place, from exp(),
+   sqrt() and IEEE division in max_ulp[0..2], and the number of cut-off violations
+   (exp below -690 -> 0, sqrt below 1e-290 -> 0) in *violations.  Synchronises `stream`. */
+int k3d_selftest_math(int64_t n, uint64_t *max_ulp, uint64_t *violations, void *stream);
+
 /* fp64 pipe peak probe: runs a dependent-chain-free DFMA loop on all SMs and returns
    the measured TFLOP/s (2 flops per DFMA).  Used only by bench.py for the roofline. */
 int k3d_measure_fp64_peak(double *tflops, double *ms, void *stream);

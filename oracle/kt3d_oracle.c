@@ -21,8 +21,9 @@
  * The dense solve: the reference calls scipy.linalg.solve (krige3d.py:592), i.e.
  * LAPACK *gesv = LU with partial (row) pivoting.  SciPy/LAPACK are third-party,
  * unpinned by the reference (setup.py:32-37); oracle_solve() restates the published
- * unblocked algorithm (dgetf2 + forward/back substitution) and flags an exactly zero
- * pivot as singular, which is when LAPACK returns info>0 and SciPy raises LinAlgError.
+ * unblocked algorithm (dgetf2 + forward/back substitution).  LAPACK returns info>0 (SciPy
+ * raises LinAlgError, krige3d.py:593) only for an exactly zero pivot; the oracle treats a
+ * pivot <= ORC_SING_TOL x the largest matrix entry as zero (repair D16, see oracle_solve).
  */
 #include <math.h>
 #include <stdint.h>
@@ -34,6 +35,7 @@
 
 #define ORC_MAXNST 4
 #define ORC_MAXDRIFT 9
+#define ORC_SING_TOL 1e-12
 #define ORC_EPS (7. / 3 - 4. / 3 - 1) /* krige3d.py:795,853 : 2.220446049250313e-16 */
 
 typedef struct {
@@ -229,6 +231,15 @@ static int orc_search(const OrcParams *p, double xloc, double yloc, double zloc,
 /* LAPACK dgetf2/dgetrs restated: LU with partial pivoting, row-major a[n*n]. */
 static int oracle_solve(int n, double *a, double *b)
 {
+    /* Repair D16: LAPACK reports a singular matrix only for an exactly zero pivot; the
+     * systems that ARE singular (duplicate samples, collinear drift columns) reach it with
+     * pivots of order 1e-16 and come back as garbage weights of order 1e16 (SciPy adds an
+     * "ill-conditioned matrix" warning, the reference prints nothing).  A pivot at or below
+     * ORC_SING_TOL times the largest matrix entry is treated as zero. */
+    double amax = 0.0;
+    for (int i = 0; i < n * n; i++)
+        if (fabs(a[i]) > amax)
+            amax = fabs(a[i]);
     for (int k = 0; k < n; k++) {
         int piv = k;
         double big = fabs(a[k * n + k]);
@@ -239,7 +250,7 @@ static int oracle_solve(int n, double *a, double *b)
                 piv = r;
             }
         }
-        if (big == 0.0 || big != big)
+        if (big <= ORC_SING_TOL * amax || big != big)
             return 1;
         if (piv != k) {
             for (int c = 0; c < n; c++) {

@@ -69,7 +69,7 @@ class K3dLaunchInfo(C.Structure):
 # every symbol include/k3d.h declares
 SYMBOLS = ("k3d_version", "k3d_last_error", "k3d_krige_slab", "k3d_krige_points",
            "k3d_build_template", "k3d_krige_slab_host", "k3d_krige_points_host", "k3d_last_launch",
-           "k3d_measure_fp64_peak")
+           "k3d_measure_fp64_peak", "k3d_release", "k3d_selftest_math")
 
 _lib = None
 
@@ -106,6 +106,11 @@ def lib():
         L.k3d_measure_fp64_peak.restype = C.c_int
         L.k3d_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double),
                                             C.c_void_p]
+        L.k3d_release.restype = C.c_int
+        L.k3d_release.argtypes = []
+        L.k3d_selftest_math.restype = C.c_int
+        L.k3d_selftest_math.argtypes = [C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                        C.c_void_p]
         _lib = L
     return _lib
 
@@ -113,6 +118,14 @@ def lib():
 def check(rc):
     if rc != 0:
         raise K3dError("k3d error %d: %s" % (rc, lib().k3d_last_error().decode()))
+
+
+def selftest_math(n, stream=None):
+    """(max ulp distance of exp_neg, sqrt_pos, rcp_fast from the CUDA library, violations)."""
+    ulp = (C.c_uint64 * 3)()
+    bad = C.c_uint64()
+    check(lib().k3d_selftest_math(int(n), ulp, C.byref(bad), C.c_void_p(stream)))
+    return [int(v) for v in ulp], int(bad.value)
 
 
 def last_launch():

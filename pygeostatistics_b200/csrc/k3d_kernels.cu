@@ -42,6 +42,12 @@
 #define K3D_VERSION_STR "pygeostatistics_b200 k3d 0.1 (sm_100a)"
 #define K3D_EPS 2.220446049250313e-16 /* 7./3-4./3-1, krige3d.py:795,853 */
 #define FULL 0xffffffffu
+// A kriging system whose elimination meets a pivot of magnitude <= K3D_SING_TOL * maxcov is
+// reported singular (K3D_ST_SINGULAR, NaN).  The reference hands such systems (duplicate
+// samples, collinear drift columns) to LAPACK, which returns garbage weights of order 1e16
+// with an "ill-conditioned matrix" warning unless the pivot is exactly zero (repair D16;
+// the oracle applies the same threshold to its pivoted LU).
+#define K3D_SING_TOL 1e-12
 #ifndef K3D_SMALL_CTAS
 #define K3D_SMALL_CTAS 3 /* resident CTAs targeted by the small-system (<= 20 rows) kernel */
 #endif
@@ -65,6 +71,16 @@ int fail(int code, const char *fmt, const char *detail = "")
 {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
+}
+
+// destroys this thread's timing events (created on g_ev_dev; destroying an event does not
+// need that device to be current)
+void drop_events()
+{
+    for (int i = 0; i < 3; i++)
+        if (g_ev[i]) { cudaEventDestroy(g_ev[i]); g_ev[i] = nullptr; }
+    g_ev_dev = -1;
+    g_ev_pending = false;
 }
 
 #define CUDA_TRY(call)                                                         \
@@ -152,8 +168,12 @@ __host__ __device__ inline int spw_bytes(const SCfg &c) { return align16(spw_off
 //         [part f64 x nsplit*napad]             block kriging: partial right-hand sides
 __host__ __device__ inline int b_off_udb(const BCfg &c) { return align16(c.ntri * 2); } // 16-byte aligned records
 __host__ __device__ inline int b_rounds_per_warp(const BCfg &c)
-{   // most rounds of 32 covariance items one node can publish: all pairs + the right-hand side
-    return ((c.ndp * (c.ndp - 1) / 2 + 31) >> 5) + c.nsplit * (c.napad >> 5);
+{   // most rounds of 32 covariance items one node can publish.  Pair rounds: the whole
+    // triangle 32 pairs at a time (full rebuild), or one round per newcomer (partial update,
+    // taken when 2 * newcomers <= na: up to ndp / 2 rounds, which exceeds the triangle's
+    // count below ndp = 32); then the right-hand side rounds.
+    const int tri_rounds = (c.ndp * (c.ndp - 1) / 2 + 31) >> 5, new_rounds = c.ndp >> 1;
+    return (tri_rounds > new_rounds ? tri_rounds : new_rounds) + c.nsplit * (c.napad >> 5);
 }
 __host__ __device__ inline int b_off_rtab(const BCfg &c) { return align16(b_off_udb(c) + c.ustride * c.ndb * 8); }
 __host__ __device__ inline int b_off_warp(const BCfg &c) { return align16(b_off_rtab(c) + c.warps * b_rounds_per_warp(c) * 2); }
@@ -321,74 +341,127 @@ __device__ __noinline__ void transform_point_cold(const K3dParams &P, const KPre
     transform_point(P, Q, x, y, z, u, stride, idx);
 }
 
-// 1/d to full double precision without the library's special-case slow path: hardware
-// seed (MUFU.RCP64H) + two Newton steps.  d == 0 gives a non-finite result, which the
-// caller reports as a singular system.
+// 1/d to (better than) double precision without the library's special-case slow path:
+// hardware seed (MUFU.RCP64H, relative error e ~ 2^-23) and one cubic step
+// y (1 + e + e^2), which leaves e^3.  d == 0 gives a non-finite result; the caller tracks the
+// magnitude of every pivot and reports tiny ones as a singular system.
 __device__ __forceinline__ double rcp_fast(double d)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
-    return y;
+    const double e = fma(-d, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 }
 
+// predicated shared stores without a branch around them (the owner lanes of a pivot row)
+__device__ __forceinline__ void sts_f64x2_if(int pred, uint32_t a, double x, double y)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p st.shared.v2.f64 [%1], {%2, %3};\n\t}"
+                 ::"r"(pred), "r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sts_f64_if(int pred, uint32_t a, double x)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p st.shared.f64 [%1], %2;\n\t}"
+                 ::"r"(pred), "r"(a), "d"(x) : "memory");
+}
+
+// Register-resident LDL^T of the bordered system.  Entry (r, c), c <= r, lives in lane
+// (r & 3) * 8 + (c & 7), register m[r >> 2][c >> 3].  A pivot row is handed to the other
+// lanes through a shared row buffer stored PERMUTED: column c at
+//     rowpos(c) = (c & 3) * 12 + ((c >> 2) & 1) * 6 + (c >> 3)
+// so that everything a lane needs is contiguous and 16-byte aligned: the columns
+// lj, lj + 8, ... it multiplies into (its own registers' columns, which is also what an
+// owner lane writes) start at rowpos(lj), and the rows li, li + 8, ... / li + 4, li + 12, ...
+// it updates are the runs of lanes lj = li and lj = li + 4.  One pivot costs 128-bit shared
+// accesses only (c3: 3 stores + 8 loads against 5 + 15 with the plain row), the owner lanes'
+// stores are predicated instead of branched around, and the pivots are entered through ONE
+// switch on the system size instead of a test per pivot.
 template <int AMAX> struct RegSolve {
     static constexpr int BMAX = ((4 * (AMAX - 1) + 3) >> 3) + 1;
+    static constexpr int UROW = 48; // doubles per row buffer (4 x 12)
+    static_assert(BMAX <= 6, "row buffer groups hold 6 columns");
 
-    // rank-1 update of row blocks 0..A-1 with the pivot row in `row`
+    static __host__ __device__ constexpr int rowpos(int c) { return (c & 3) * 12 + ((c >> 2) & 1) * 6 + (c >> 3); }
+
+    // rank-1 update of row blocks 0..A-1 with the pivot row at shared address `row`
     template <int A>
-    static __device__ __forceinline__ void update(double (&m)[AMAX][BMAX], const double *row,
-                                                  int li, int lj, double ninv)
+    static __device__ __forceinline__ void update(double (&m)[AMAX][BMAX], uint32_t row,
+                                                  uint32_t abi, uint32_t abj, double ninv)
     {
-        constexpr int B = ((4 * (A - 1) + 3) >> 3) + 1;
-        double u[B];
+        if constexpr (A > 0) {
+            constexpr int B = ((4 * (A - 1) + 3) >> 3) + 1;
+            double u[B + 1];
 #pragma unroll
-        for (int b = 0; b < B; b++) u[b] = row[lj + 8 * b] * ninv;
+            for (int b = 0; b < B; b += 2) {
+                if (b + 1 < B) {
+                    const double2 t = lds_f64x2(row + abj + 8 * b);
+                    u[b] = t.x * ninv;
+                    u[b + 1] = t.y * ninv;
+                } else {
+                    u[b] = lds_f64(row + abj + 8 * b) * ninv;
+                }
+            }
 #pragma unroll
-        for (int a = 0; a < A; a++) {
-            const double w = row[li + 4 * a]; // one at a time: registers are the limit
+            for (int par = 0; par < 2; par++) {      // rows li + 8 e (+ 4): a = 2 e + par
 #pragma unroll
-            for (int b = 0; b < B; b++)
-                if (8 * b <= 4 * a + 3) m[a][b] = fma(w, u[b], m[a][b]);
+                for (int e = 0; 2 * e + par < A; e += 2) {
+                    const int a0 = 2 * e + par, a1 = a0 + 2;
+                    double w0, w1 = 0.0;
+                    if (a1 < A) {
+                        const double2 t = lds_f64x2(row + abi + 8 * (6 * par + e));
+                        w0 = t.x;
+                        w1 = t.y;
+                    } else {
+                        w0 = lds_f64(row + abi + 8 * (6 * par + e));
+                    }
+#pragma unroll
+                    for (int b = 0; b < B; b++)
+                        if (8 * b <= 4 * a0 + 3) m[a0][b] = fma(w0, u[b], m[a0][b]);
+                    if (a1 < A) {
+#pragma unroll
+                        for (int b = 0; b < B; b++)
+                            if (8 * b <= 4 * a1 + 3) m[a1][b] = fma(w1, u[b], m[a1][b]);
+                    }
+                }
+            }
         }
     }
 
-    // Pivots M = 4*AP+3 .. 4*AP (those that exist).  Their rows live in register block AP
-    // of the lanes with li == M & 3.  The update always covers blocks 0..AP: for the last
-    // pivot of the block (q == 0) block AP then holds only rows already eliminated
-    // (don't-care values), which keeps one code path per AP.
-    template <int AP>
-    static __device__ __forceinline__ void block(double (&m)[AMAX][BMAX], int R, double *rowbuf,
-                                                 int urow, int li, int lj)
+    // Pivot M: its row lives in register block AP = M >> 2 of the lanes with li == M & 3.
+    // The update covers blocks 0..AP (0..AP-1 when M is the first row of its block: the
+    // block's other rows are eliminated already); rows of block AP beyond the pivot then
+    // hold don't-care values, which keeps one code path per pivot.
+    template <int M>
+    static __device__ __forceinline__ void pivot(double (&m)[AMAX][BMAX], uint32_t rowbuf, int li,
+                                                 uint32_t abi, uint32_t abj, unsigned &minhi)
     {
-        if constexpr (AP >= 0) {
-            if (4 * AP <= R) { // uniform: does this row block exist in the system?
-#pragma unroll // (rolled, the loop control and row addressing cost 10 % of the kernel)
-                for (int q = 3; q >= 0; q--) {
-                    const int M = 4 * AP + q;
-                    if (M > R || M < 2) continue;
-                    double *row = rowbuf + (M & 1) * urow;
-                    if (li == q) {
+        if constexpr (M >= 2 && M < 4 * AMAX) {
+            constexpr int AP = M >> 2, q = M & 3;
+            constexpr int BW = ((4 * AP + 3) >> 3) + 1; // column blocks of row block AP
+            const uint32_t row = rowbuf + (M & 1) * (UROW * 8);
+            const int own = li == q;
 #pragma unroll
-                        for (int b = 0; b < BMAX; b++)
-                            if (8 * b <= 4 * AP + 3) row[lj + 8 * b] = m[AP][b];
-                    }
-                    __syncwarp();
-                    update<AP + 1>(m, row, li, lj, -rcp_fast(row[M]));
-                }
+            for (int b = 0; b < BW; b += 2) {
+                if (b + 1 < BW) sts_f64x2_if(own, row + abj + 8 * b, m[AP][b], m[AP][b + 1]);
+                else sts_f64_if(own, row + abj + 8 * b, m[AP][b]);
             }
-            block<AP - 1>(m, R, rowbuf, urow, li, lj);
+            __syncwarp();
+            const double d = lds_f64(row + 8 * rowpos(M));
+            minhi = min(minhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+            const double ninv = -rcp_fast(d);
+            update<(q == 0 ? AP : AP + 1)>(m, row, abi, abj, ninv);
         }
     }
 
     // Eliminates pivots M = R .. 2; leaves var = entry (1,1) and est = -entry (1,0).
-    static __device__ __forceinline__ void run(const double *Pm, int R, double *rowbuf, int urow,
-                                               int lane, double &est, double &var)
+    // minhi: smallest |pivot| seen (high word of the double, which orders like the value).
+    static __device__ __forceinline__ void run(const double *Pm, int R, double *rowbuf_g, int lane,
+                                               double &est, double &var, unsigned &minhi)
     {
         const int li = lane >> 3, lj = lane & 7;
+        const uint32_t abi = (uint32_t)(li * 12) * 8, abj = (uint32_t)((lj & 3) * 12 + (lj >> 2) * 6) * 8;
+        const uint32_t rowbuf = smem_u32(rowbuf_g);
         double m[AMAX][BMAX];
 #pragma unroll
         for (int a = 0; a < AMAX; a++)
@@ -398,7 +471,18 @@ template <int AMAX> struct RegSolve {
                     int r = li + 4 * a, c = lj + 8 * b;
                     m[a][b] = (c <= r && r <= R) ? Pm[pk(r, c)] : 0.0;
                 }
-        block<AMAX - 1>(m, R, rowbuf, urow, li, lj);
+        minhi = 0x7fffffffu;
+#define K3D_PIV(M) case M: pivot<M>(m, rowbuf, li, abi, abj, minhi); /* falls through */
+        switch (R) { // R <= 4 * AMAX - 1 (amax_for)
+        K3D_PIV(43) K3D_PIV(42) K3D_PIV(41) K3D_PIV(40) K3D_PIV(39) K3D_PIV(38) K3D_PIV(37) K3D_PIV(36)
+        K3D_PIV(35) K3D_PIV(34) K3D_PIV(33) K3D_PIV(32) K3D_PIV(31) K3D_PIV(30) K3D_PIV(29) K3D_PIV(28)
+        K3D_PIV(27) K3D_PIV(26) K3D_PIV(25) K3D_PIV(24) K3D_PIV(23) K3D_PIV(22) K3D_PIV(21) K3D_PIV(20)
+        K3D_PIV(19) K3D_PIV(18) K3D_PIV(17) K3D_PIV(16) K3D_PIV(15) K3D_PIV(14) K3D_PIV(13) K3D_PIV(12)
+        K3D_PIV(11) K3D_PIV(10) K3D_PIV(9) K3D_PIV(8) K3D_PIV(7) K3D_PIV(6) K3D_PIV(5) K3D_PIV(4)
+        K3D_PIV(3) K3D_PIV(2)
+        default: break;
+        }
+#undef K3D_PIV
         var = __shfl_sync(FULL, m[0][0], 9);   // (r,c) = (1,1): lane 1*8+1
         est = -__shfl_sync(FULL, m[0][0], 8);  // (r,c) = (1,0): lane 1*8+0
     }
@@ -407,11 +491,14 @@ template <int AMAX> struct RegSolve {
 // Generic fallback for systems too large for the register solver: the same elimination
 // on a scratch copy of the packed triangle in shared memory (flat rank-1 updates).
 __device__ __forceinline__ void smem_solve(double *Pm, const uint16_t *tri, int R, double *wv,
-                                           int lane, double &est, double &var)
+                                           int lane, double &est, double &var, unsigned &minhi)
 {
+    minhi = 0x7fffffffu;
     for (int M = R; M >= 2; M--) {
         const int T = (M * (M + 1)) >> 1;
-        const double inv = 1.0 / Pm[T + M];
+        const double d = Pm[T + M];
+        minhi = min(minhi, (unsigned)__double2hiint(d) & 0x7fffffffu);
+        const double inv = 1.0 / d;
         for (int j = lane; j < M; j += 32) wv[j] = Pm[T + j] * inv;
         __syncwarp();
         const double *u = Pm + T;
@@ -1125,6 +1212,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     const size_t slab_off = (size_t)iz0 * P.nx * P.ny;
     const unsigned ltm = (1u << lane) - 1u;
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    const unsigned singhi = (unsigned)__double2hiint(K3D_SING_TOL * P.maxcov); // |pivot| test, high word
     const int mdt = P.mdt;
     // block kriging: a sample's ndb block-point covariances are split into nsplit work items
     // of a few points so that the pooled rounds stay evenly sized; the partial sums are added
@@ -1449,14 +1537,17 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 __syncwarp();
 
                 // ---- 3. LDL^T elimination of the N pivots ---------------------------
+                unsigned minhi;
                 if constexpr (AMAX > 0) {
-                    RegSolve<AMAX>::run(Pm, R, rows, cfg.urow, lane, est, var);
+                    RegSolve<AMAX>::run(Pm, R, rows, lane, est, var, minhi);
                     nprev = na;
                 } else {
-                    smem_solve(Pm, tri, R, rows, lane, est, var); // destroys Pm
+                    smem_solve(Pm, tri, R, rows, lane, est, var, minhi); // destroys Pm
                     nprev = -1;
                 }
-                if (!isfinite(est) || !isfinite(var)) { // zero pivot (krige3d.py:593)
+                // krige3d.py:593 "Singular matrix" (repair D16): a pivot below 1e-12 maxcov,
+                // or a non-finite result
+                if (minhi <= singhi || !isfinite(est) || !isfinite(var)) {
                     status = K3D_ST_SINGULAR;
                     est = var = NaN;
                 } else {
@@ -1523,6 +1614,58 @@ __global__ void k3d_dfma_probe(double *sink, int iters)
     }
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456) sink[0] = s;
+}
+
+// ---------------------------------------------------------------------------
+// self test of the in-line math (exp_neg, sqrt_pos, rcp_fast) against the CUDA library
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{   // splitmix64
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(unsigned long long z) { return (double)(z >> 11) * 0x1.0p-53; }
+__device__ __forceinline__ unsigned long long ulp_dist(double a, double b)
+{   // both finite and of the same sign on the tested domains
+    const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+    return (unsigned long long)(ia > ib ? ia - ib : ib - ia);
+}
+
+// out[0..2]: largest distance in units in the last place between exp_neg / sqrt_pos / rcp_fast
+// and exp / sqrt / IEEE division; out[3]: number of cut-off violations (exp_neg below -690
+// must return 0 or agree to 1e-300 absolute; sqrt_pos below 1e-290 must return 0)
+__global__ void k3d_selftest_kernel(long long n, unsigned long long *out)
+{
+    __shared__ double tab[32];
+    if (threadIdx.x < 32) tab[threadIdx.x] = exp2((double)threadIdx.x * 0.03125);
+    __syncthreads();
+    unsigned long long e0 = 0, e1 = 0, e2 = 0, bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long h = mix64((unsigned long long)i);
+        // exp_neg on [-690, 0]: uniform, plus a share concentrated near 0 and near the cut-off
+        double x = -690.0 * u01(h);
+        if ((i & 7) == 1) x = -u01(mix64(h)) * 1e-3;
+        if ((i & 7) == 2) x = -689.0 - u01(mix64(h));
+        e0 = max(e0, ulp_dist(exp_neg(x, tab), exp(x)));
+        const double xc = -690.0 - 60.0 * u01(mix64(h ^ 1));   // beyond the cut-off
+        const double yc = exp_neg(xc, tab);
+        if (!(yc == 0.0 || fabs(yc - exp(xc)) <= 1e-300)) bad++;
+        // sqrt_pos on [1e-290, 1e6], log-uniform (the covariance sees (h/a)^2)
+        const double a = exp(log(1e-290) + (log(1e6) - log(1e-290)) * u01(mix64(h ^ 2)));
+        e1 = max(e1, ulp_dist(sqrt_pos(a), sqrt(a)));
+        if (sqrt_pos(1e-291 * u01(mix64(h ^ 3))) != 0.0) bad++;
+        // rcp_fast on +-[1e-150, 1e150], log-uniform (pivots of the elimination)
+        double d = exp(log(1e-150) + (log(1e150) - log(1e-150)) * u01(mix64(h ^ 4)));
+        if (h & 1) d = -d;
+        e2 = max(e2, ulp_dist(rcp_fast(d), 1.0 / d));
+    }
+    atomicMax(&out[0], e0);
+    atomicMax(&out[1], e1);
+    atomicMax(&out[2], e2);
+    atomicAdd(&out[3], bad);
 }
 
 int roundup32(int x) { return (x + 31) & ~31; }
@@ -1600,7 +1743,7 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
     c->has_ext = (p->ktype == 2 || p->ktype == 3) ? 1 : 0;
     c->need_xyz = (p->mdt > 1 || p->ndb > 1) ? 1 : 0;
     const int amax = amax_for(c->rtot);
-    c->urow = amax > 0 ? 8 * (((4 * (amax - 1) + 3) >> 3) + 1) : c->rtot;
+    c->urow = amax > 0 ? 48 : c->rtot; // RegSolve<>::UROW (permuted row: 4 groups of 12)
     c->reuse = amax > 0 ? 1 : 0;
     c->napad = (p->ndmax + 31) & ~31;
     c->nsplit = 1;
@@ -1659,10 +1802,13 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
 // that keeps what it has been given (release threshold = max): the default pool hands
 // freed memory back to the OS at the next synchronisation, which costs more than the
 // search kernel itself when 2 GB are re-allocated on every call.
+std::mutex g_pool_mu;
+cudaMemPool_t g_pools[64] = {};
+
 int scratch_pool(int dev, cudaMemPool_t *pool)
 {
-    static std::mutex mu;
-    static cudaMemPool_t pools[64] = {};
+    std::mutex &mu = g_pool_mu;
+    cudaMemPool_t *pools = g_pools;
     if (dev < 0 || dev >= 64) return fail(K3D_EINVAL, "device index out of range");
     std::lock_guard<std::mutex> lock(mu);
     if (!pools[dev]) {
@@ -1679,13 +1825,35 @@ int scratch_pool(int dev, cudaMemPool_t *pool)
     return K3D_OK;
 }
 
+// The kernels' dynamic shared memory limit is raised ONCE per kernel and device, to the
+// device maximum (a per-call value would race between host threads with different plans).
+int raise_smem_limit(const void *func, int dev, int smem_max)
+{
+    static std::mutex mu;
+    static const void *done[64][16] = {};
+    if (dev < 0 || dev >= 64) return fail(K3D_EINVAL, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    int i = 0;
+    for (; i < 16 && done[dev][i]; i++)
+        if (done[dev][i] == func) return K3D_OK;
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, func)); // static + dynamic must fit the opt-in maximum
+    CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  smem_max - (int)fa.sharedSizeBytes));
+    if (i < 16) done[dev][i] = func;
+    return K3D_OK;
+}
+
 template <int AMAX, bool BLOCK>
 int launch_solve2(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
                   int iz0, int iz1, const int32_t *nbr, int32_t *cnt, const BCfg &c,
                   long long ntiles, cudaStream_t st, const PtSet &ps)
 {
-    CUDA_TRY(cudaFuncSetAttribute(k3d_solve_kernel<AMAX, BLOCK>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+    int dev = 0, smem_max = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int rc = raise_smem_limit((const void *)k3d_solve_kernel<AMAX, BLOCK>, dev, smem_max);
+    if (rc) return rc;
     k3d_solve_kernel<AMAX, BLOCK><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(
         *p, *q, *in, *out, iz0, iz1, nbr, cnt, c, ps);
     CUDA_TRY(cudaGetLastError());
@@ -1736,8 +1904,11 @@ static int validate(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_
     if (p->ndb < 1 || p->ndb > K3D_MAXDIS) return fail(K3D_EINVAL, "ndb outside 1..K3D_MAXDIS");
     if (p->ktype < 0 || p->ktype > 3) return fail(K3D_EINVAL, "ikrige outside 0..3");
     if (p->noct < 0 || 8 * p->noct > 512) return fail(K3D_EINVAL, "noct outside 0..64");
-    for (int i = 0; i < p->nst; i++)
+    for (int i = 0; i < p->nst; i++) {
         if (p->it[i] < 1 || p->it[i] > 5) return fail(K3D_EINVAL, "variogram type outside 1..5");
+        if (p->it[i] != 4 && !(p->aa[i] > 0.0)) return fail(K3D_EINVAL, "variogram range must be positive");
+    }
+    if (!(p->radsqd > 0.0)) return fail(K3D_EINVAL, "search radius must be positive");
     if (p->mdt < 0 || p->mdt > K3D_MAXDRIFT + 2) return fail(K3D_EINVAL, "bad mdt");
     if (!in->sx || !in->sy || !in->sz || !in->sv || !in->sbstart || !in->runs ||
         !in->nodex0 || !in->nodey0 || !in->nodez0 || !in->dbxyz)
@@ -1784,10 +1955,9 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
     if (ntiles > 0x7fffffffLL) return fail(K3D_EINVAL, "too many tiles");
     KPrep q;
     make_prep(p, &q);
-    CUDA_TRY(cudaFuncSetAttribute(k3d_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  sc.smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(k3d_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  sc.smem_bytes));
+    if ((rc = raise_smem_limit((const void *)k3d_search_kernel<false>, dev, smem_max)) != K3D_OK ||
+        (rc = raise_smem_limit((const void *)k3d_search_kernel<true>, dev, smem_max)) != K3D_OK)
+        return rc;
 
     // neighbour lists travel from the search kernel to the solve kernel through global
     // memory: the caller's arrays when given, else stream-ordered scratch, at most ~4 GB at
@@ -1809,6 +1979,7 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
         }
     }
     if (g_ev_dev != dev) { // per-thread timing events for k3d_last_launch
+        drop_events();
         for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&g_ev[i]));
         g_ev_dev = dev;
     }
@@ -1818,10 +1989,17 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
         rc = scratch_pool(dev, &pool);
         if (rc) return rc;
     }
-    if (!out->nbr_idx)
-        CUDA_TRY(cudaMallocFromPoolAsync((void **)&snbr, (size_t)zstep * plane * p->ndmax * 4, pool, st));
-    if (!out->nbr_cnt)
-        CUDA_TRY(cudaMallocFromPoolAsync((void **)&scnt, (size_t)zstep * plane * 4, pool, st));
+    if (!out->nbr_idx &&
+        cudaMallocFromPoolAsync((void **)&snbr, (size_t)zstep * plane * p->ndmax * 4, pool, st) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(K3D_ENOMEM, "neighbour-list scratch allocation failed");
+    }
+    if (!out->nbr_cnt &&
+        cudaMallocFromPoolAsync((void **)&scnt, (size_t)zstep * plane * 4, pool, st) != cudaSuccess) {
+        cudaGetLastError();
+        if (snbr) cudaFreeAsync(snbr, st);
+        return fail(K3D_ENOMEM, "neighbour-count scratch allocation failed");
+    }
     for (int za = iz0; za < iz1 && rc == K3D_OK; za += zstep) {
         const int zb = za + zstep < iz1 ? za + zstep : iz1;
         const size_t shift = (size_t)(za - iz0) * plane; // nodes before this run in the slab
@@ -1930,6 +2108,39 @@ int k3d_measure_fp64_peak(double *tflops, double *ms, void *stream)
     return K3D_OK;
 }
 
+int k3d_release(void)
+{
+    drop_events();
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    int rc = K3D_OK;
+    for (int dev = 0; dev < 64; dev++)
+        if (g_pools[dev] && cudaMemPoolTrimTo(g_pools[dev], 0) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(K3D_ECUDA, "cudaMemPoolTrimTo failed");
+        }
+    return rc;
+}
+
+int k3d_selftest_math(int64_t n, uint64_t *max_ulp, uint64_t *violations, void *stream)
+{
+    if (n < 1 || !max_ulp || !violations) return fail(K3D_EINVAL, "bad self-test arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *d = nullptr, h[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMalloc(&d, sizeof(h)));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(h), st);
+    if (e == cudaSuccess) {
+        k3d_selftest_kernel<<<148 * 4, 256, 0, st>>>((long long)n, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(K3D_ECUDA, "math self test: %s", cudaGetErrorString(e));
+    max_ulp[0] = h[0]; max_ulp[1] = h[1]; max_ulp[2] = h[2];
+    *violations = h[3];
+    return K3D_OK;
+}
+
 // Host-buffer variant of both entry points: one device arena, copies in, the kernels,
 // copies out, one synchronisation.
 static int krige_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_t iz1,
@@ -1962,6 +2173,7 @@ static int krige_host(const K3dParams *p, const K3dInputs *in, int32_t iz0, int3
     size_t o_st = take(out->status ? nodes : 0), o_ca = take(out->ncand ? nodes * 4 : 0);
     unsigned char *d = nullptr;
     if (cudaMalloc(&d, off ? off : 256) != cudaSuccess) {
+        cudaGetLastError(); // (the failed allocation must not surface in the next call)
         cudaStreamDestroy(st);
         return fail(K3D_ENOMEM, "device allocation failed");
     }

@@ -1,0 +1,288 @@
+"""GPU robustness: what the round-1 review found untested.
+
+  * config 5 at its stated size (1M samples, 512x512x256, block KED) on sampled nodes,
+    and its neighbour lists on slabs cut where an 8-GPU run cuts them;
+  * small ndmax on large tiles (many warps per CTA, partial updates with more rounds than
+    the triangle has: the round-table capacity);
+  * degenerate kriging systems (duplicate samples, collinear drift, constant external
+    drift): K3D_ST_SINGULAR and the oracle's NaN pattern;
+  * the in-line device math against the CUDA library;
+  * every K3D_E* return code of the C ABI that can be provoked without breaking the context.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import k3d_configs
+from oracle import kt3d_oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from test_gpu_parity import compare, gpu_run, oracle_run, _edge_par, _edge_data  # noqa: E402
+
+
+def _sampled_nodes(par, n, planes=(), seed=7):
+    nodes = par['nx'] * par['ny'] * par['nz']
+    plane = par['nx'] * par['ny']
+    rng = np.random.default_rng(seed)
+    pick = [rng.choice(nodes, n, replace=False)]
+    corners = [ix + par['nx'] * (iy + par['ny'] * iz)
+               for ix in (0, par['nx'] - 1) for iy in (0, par['ny'] - 1) for iz in (0, par['nz'] - 1)]
+    pick.append(np.array(corners))
+    for z in planes:  # nodes on both sides of the z-slab cuts of an 8-GPU run
+        pick.append(z * plane + rng.choice(plane, 64, replace=False))
+    return np.unique(np.concatenate(pick))
+
+
+def test_full_size_c5_sampled_nodes_against_oracle():
+    """BASELINE.json configs[4] as stated: 1M samples, 512x512x256, block kriging 4x4x2 with
+    external drift (stage capacity 2048, eight right-hand-side parts per sample)."""
+    par, data, sec = k3d_configs.config("c5", 1.0)
+    k = gpu_run(par, data, sec, neighbours=False)
+    cuts = [z for c in range(32, 256, 32) for z in (c - 1, c)]
+    node_list = _sampled_nodes(par, 6000, planes=cuts)
+    st, ores = oracle_run(par, data, sec, node_list=node_list, threads=16)
+    vmax = float(np.max(np.abs(data['v'])))
+    compare(k, st, ores, node_list=node_list, vmax=vmax, check_neighbours=False)
+    assert np.all(k.status[~np.isnan(k.estimation)] == 0)
+    # neighbour lists: the same kernels on the slabs an 8-GPU run gives ranks 0, 1 and 7
+    P = k._params_struct()
+    host = k._host_inputs()
+    plane = par['nx'] * par['ny']
+    ext = k._external_grid()
+    est, var, nbr, cnt = ores
+    for iz0, iz1 in ((0, 2), (30, 34), (254, 256)):
+        d = k._upload(host, ext[iz0 * plane: iz1 * plane].pin_memory())
+        out = k._alloc_outputs((iz1 - iz0) * plane, neighbours=True)
+        k._launch(P, d, iz0, iz1, out)
+        torch.cuda.synchronize()
+        sel = np.nonzero((node_list >= iz0 * plane) & (node_list < iz1 * plane))[0]
+        assert len(sel) > 0
+        loc = node_list[sel] - iz0 * plane
+        g_idx = out['nbr_idx'].cpu().numpy().reshape(-1, par['ndmax'])[loc]
+        assert np.array_equal(g_idx, nbr[sel])
+        assert np.array_equal(out['nbr_cnt'].cpu().numpy()[loc], cnt[sel])
+        ge = out['est'].cpu().numpy()[loc]
+        ok = ~np.isnan(est[sel])
+        assert np.array_equal(np.isnan(ge), ~ok)
+        assert np.all(np.abs(ge[ok] - est[sel][ok]) <= 1e-9 * np.abs(est[sel][ok]) + 1e-12 * vmax)
+
+
+@pytest.mark.parametrize("ndmax,ikrige", [(4, 0), (8, 0), (8, 1), (12, 1)])
+def test_small_ndmax_on_large_tiles(ndmax, ikrige, monkeypatch):
+    """Tiles of 8x8x2 nodes worked by CTAs of 8 warps (the planner would pick 2-warp CTAs
+    here; the shape is forced), about one sample per six nodes: a node with 2-4 newcomers
+    publishes more pair rounds than the triangle of an ndmax<29 system has."""
+    monkeypatch.setenv("K3D_SOLVE_SHAPE", "3,8")
+    par = dict(k3d_configs.BASE)
+    par.update(nx=400, ny=400, nz=16, ikrige=ikrige, ndmax=ndmax, radius_hmax=3.0,
+               radius_hmin=3.0, radius_vert=3.0, aa_hmax=[6.0], aa_hmin=[6.0], aa_vert=[6.0])
+    rng = np.random.default_rng(21)
+    n = 400 * 400 * 16 // 6
+    p = rng.uniform(0, 1, (n, 3)) * np.array([400.0, 400.0, 16.0])
+    data = {'x': p[:, 0].copy(), 'y': p[:, 1].copy(), 'z': p[:, 2].copy(), 'v': rng.normal(size=n)}
+    k = gpu_run(par, data, None)
+    from pygeostatistics_b200 import _native
+    assert _native.last_launch()['warps_per_cta'] == 8
+    node_list = _sampled_nodes(par, 120000)
+    st, ores = oracle_run(par, data, None, node_list=node_list, threads=16)
+    compare(k, st, ores, node_list=node_list, vmax=float(np.max(np.abs(data['v']))))
+
+
+def _status_count(k, code):
+    return int((k.status == code).sum())
+
+
+def test_duplicate_samples_are_singular():
+    """Two samples at identical coordinates make two identical rows.  LAPACK (the reference's
+    scipy.linalg.solve) meets a pivot of order 1e-16 and returns weights of order 1e16;
+    both the oracle and the GPU path report the system singular (repair D16)."""
+    for ikrige in (0, 1):
+        par = _edge_par(ikrige=ikrige, ndmax=8)
+        data = _edge_data(120)
+        for c in 'xyz':
+            data[c][1] = data[c][0]
+        data['v'][1] = data['v'][0] + 1.0
+        k = gpu_run(par, data, None)
+        st, ores = oracle_run(par, data, None)
+        compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+        nsing = _status_count(k, 3)
+        assert nsing > 0
+        assert np.all(np.isnan(k.estimation[k.status == 3]))
+        # exactly the nodes that use both copies
+        both = (k.neighbours == 0).any(axis=1) & (k.neighbours == 1).any(axis=1)
+        assert np.array_equal(both & (k.neighbour_count > 1), k.status == 3)
+
+
+def test_collinear_drift_is_singular():
+    """z drift with every datum on one plane: the drift column is a multiple of the
+    unbiasedness column at every node."""
+    par = _edge_par(ikrige=1, ndmax=10, idrift=[False, False, True] + [False] * 6)
+    data = _edge_data(200)
+    data['z'][:] = 2.5
+    k = gpu_run(par, data, None)
+    st, ores = oracle_run(par, data, None)
+    compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+    assert np.isnan(k.estimation).all()
+    assert _status_count(k, 3) > 0.5 * len(k.estimation)
+    assert _status_count(k, 0) == 0
+
+
+def test_ked_with_constant_external_variable_is_singular():
+    """SURVEY.md 8c acceptance gate: KED with a constant external variable is rejected."""
+    par, data, sec = k3d_configs.config("c5", 0.05)
+    par = dict(par, nxdis=1, nydis=1, nzdis=1)
+    data = dict(data)
+    data['sec'] = np.full_like(data['sec'], 7.0)
+    sec = np.full_like(sec, 7.0)
+    k = gpu_run(par, data, sec)
+    st, ores = oracle_run(par, data, sec)
+    compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+    assert np.isnan(k.estimation).all()
+    assert _status_count(k, 3) > 0 and _status_count(k, 0) == 0
+
+
+def test_inline_device_math_against_cuda_library():
+    """exp_neg / sqrt_pos / rcp_fast replace libm on the parity-critical path (covariance,
+    pivots).  Bound asserted: 1 ulp from the CUDA library's exp, sqrt and IEEE division on
+    2e7 points each (x in [-690, 0], a in [1e-290, 1e6], |d| in [1e-150, 1e150]), and the
+    cut-offs behave."""
+    from pygeostatistics_b200 import _native
+    ulp, bad = _native.selftest_math(20_000_000, torch.cuda.current_stream().cuda_stream)
+    print("max ulp distance: exp_neg %d, sqrt_pos %d, rcp_fast %d; violations %d"
+          % (ulp[0], ulp[1], ulp[2], bad))
+    assert bad == 0
+    assert ulp[0] <= 1 and ulp[1] <= 1 and ulp[2] <= 1, ulp
+
+
+def _abi_case():
+    par, data, sec = k3d_configs.config("c3", 0.08)
+    k = gpu_run(par, data, sec, neighbours=False)
+    d = k._upload(k._host_inputs(), None)
+    nodes = par['nx'] * par['ny'] * par['nz']
+    out = k._alloc_outputs(nodes, neighbours=False)
+    return par, k, d, out
+
+
+def test_c_abi_error_codes():
+    from pygeostatistics_b200 import _native
+    L = _native.lib()
+    par, k, d, out = _abi_case()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def call(P=None, I=None, O=None, iz0=0, iz1=None):
+        P = k._params_struct() if P is None else P
+        I = k._inputs_struct(d) if I is None else I
+        O = k._outputs_struct(out) if O is None else O
+        return L.k3d_krige_slab(C.byref(P), C.byref(I), iz0, par['nz'] if iz1 is None else iz1,
+                                C.byref(O), stream)
+
+    assert call() == 0
+    EINVAL, ENOMEM = -1, -3
+    # NULL arguments
+    assert L.k3d_krige_slab(None, None, 0, 1, None, stream) == EINVAL
+    assert b"NULL" in L.k3d_last_error()
+    # bad slab
+    assert call(iz0=3, iz1=2) == EINVAL
+    assert call(iz1=par['nz'] + 1) == EINVAL
+    # each parameter check
+    for field, value in (("nx", 0), ("ndmax", 0), ("ndmax", _native.MAXNDMAX + 1),
+                         ("nst", 0), ("nst", _native.MAXNST + 1), ("ndb", 0),
+                         ("ndb", _native.MAXDIS + 1), ("ktype", 4), ("noct", 65), ("mdt", 12),
+                         ("radsqd", 0.0)):
+        P = k._params_struct()
+        setattr(P, field, value)
+        assert call(P=P) == EINVAL, field
+        assert len(L.k3d_last_error()) > 0
+    P = k._params_struct()
+    P.it[0] = 6
+    assert call(P=P) == EINVAL
+    P = k._params_struct()
+    P.aa[0] = 0.0                      # range 0 would make every covariance non-finite
+    assert call(P=P) == EINVAL
+    # missing arrays
+    I = k._inputs_struct(d)
+    I.sx = None
+    assert call(I=I) == EINVAL
+    O = k._outputs_struct(out)
+    O.est = None
+    assert call(O=O) == EINVAL
+    P = k._params_struct()
+    P.ktype = 3                         # external drift without ssec / extgrid
+    P.mdt = 2
+    assert call(P=P) == EINVAL
+    # an empty slab is not an error
+    assert call(iz0=2, iz1=2) == 0
+    # listed locations
+    Q = _native.K3dPoints()
+    Q.npts = -1
+    P = k._params_struct()
+    I = k._inputs_struct(d)
+    O = k._outputs_struct(out)
+    assert L.k3d_krige_points(C.byref(P), C.byref(I), C.byref(Q), C.byref(O), stream) == EINVAL
+    Q.npts = 5                          # arrays missing
+    assert L.k3d_krige_points(C.byref(P), C.byref(I), C.byref(Q), C.byref(O), stream) == EINVAL
+    assert L.k3d_krige_points(C.byref(P), C.byref(I), None, C.byref(O), stream) == EINVAL
+    # template builder and probes
+    assert L.k3d_build_template(0, 1, 1, 1.0, 1.0, 1.0, None, 1.0, None, stream) == EINVAL
+    assert L.k3d_last_launch(None) == EINVAL
+    assert L.k3d_measure_fp64_peak(None, None, stream) == EINVAL
+    assert L.k3d_selftest_math(0, None, None, stream) == EINVAL
+    # K3D_ENOMEM: a host-buffer call whose device arena cannot be allocated (nothing is
+    # copied before the allocation succeeds)
+    P = k._params_struct()
+    P.nx = P.ny = P.nz = 1 << 15
+    s = k.searcher
+    arrs = dict(sx=np.ascontiguousarray(k.vr['x']), sy=np.ascontiguousarray(k.vr['y']),
+                sz=np.ascontiguousarray(k.vr['z']), sv=np.ascontiguousarray(k.vr['v']),
+                sbstart=s.sbstart, runs=np.ascontiguousarray(s.runs.reshape(-1)),
+                nodex0=s.nodex0, nodey0=s.nodey0, nodez0=s.nodez0,
+                dbxyz=np.concatenate([k.xdb, k.ydb, k.zdb]))
+    I = _native.K3dInputs()
+    I.nd = len(arrs['sx'])
+    for name, a in arrs.items():
+        setattr(I, name, a.ctypes.data)
+    I.nruns, I.ntmpl = len(s.runs), s.nsbtosr
+    dummy = np.empty(8)
+    O = _native.K3dOutputs()
+    O.est = O.var = dummy.ctypes.data
+    assert L.k3d_krige_slab_host(C.byref(P), C.byref(I), 0, 1 << 15, C.byref(O)) == ENOMEM
+    assert b"alloc" in L.k3d_last_error()
+    # the context is still healthy, and k3d_release() gives the scratch back
+    assert call() == 0
+    torch.cuda.synchronize()
+    assert L.k3d_release() == 0
+    assert call() == 0
+    torch.cuda.synchronize()
+
+
+def test_largest_supported_system():
+    """ndmax 64 with nine drift terms, external drift, four structures and a 5x5x5 block:
+    either the plan fits (then it must agree with the oracle) or the call says
+    K3D_ECAPACITY -- never a crash."""
+    from pygeostatistics_b200 import _native
+    par = _edge_par(ikrige=3, ndmax=64, nxdis=5, nydis=5, nzdis=5, idrift=[True] * 9, nst=4,
+                    it=[1, 2, 3, 1], cc=[0.2, 0.3, 0.2, 0.2], c0=0.1, ang1=[0.0, 30.0, 60.0, 90.0],
+                    ang2=[0.0] * 4, ang3=[0.0] * 4, aa_hmax=[6.0, 9.0, 12.0, 20.0],
+                    aa_hmin=[6.0, 6.0, 10.0, 15.0], aa_vert=[6.0, 4.0, 8.0, 10.0],
+                    radius_hmax=6.0, radius_hmin=6.0, radius_vert=6.0, iseccol=0)
+    data = _edge_data(900)
+    data['sec'] = k3d_configs.external_field(data['x'], data['y'], data['z'])
+    gz, gy, gx = np.meshgrid(0.5 + np.arange(par['nz']), 0.5 + np.arange(par['ny']),
+                             0.5 + np.arange(par['nx']), indexing='ij')
+    sec = k3d_configs.external_field(gx, gy, gz).ravel()
+    try:
+        k = gpu_run(par, data, sec)
+    except _native.K3dError as e:
+        assert "error -4" in str(e)
+        return
+    st, ores = oracle_run(par, data, sec)
+    # 75 equations with quadratic drift: conditioning limits the agreement of two different
+    # eliminations; the NaN pattern and the neighbour lists are exact
+    est, var, nbr, cnt = ores
+    assert np.array_equal(k.neighbours_sorted_space, nbr.astype(np.int64))
+    assert np.array_equal(np.isnan(k.estimation), np.isnan(est))
+    ok = ~np.isnan(est)
+    assert np.allclose(k.estimation[ok], est[ok], rtol=1e-6, atol=1e-8)
