@@ -51,9 +51,8 @@
 #ifndef K3D_SMALL_CTAS
 #define K3D_SMALL_CTAS 3 /* resident CTAs targeted by the small-system (<= 20 rows) kernel */
 #endif
-#ifndef K3D_NHINT
-#define K3D_NHINT 32 /* previous node's neighbours re-measured for the search bounds (<= 32) */
-#endif
+#define K3D_SBINS 64  /* search: bins (in squared distance from the tile centre) of the candidates */
+#define K3D_SCHUNK 16 /* search: candidates between two termination tests */
 // The warps of a CTA move through the phases of a node together (search+fill /
 // covariances / solve): warps that run the same loop share instruction-cache lines, which
 // measured as the difference between 2.5 and 0.2 "no instruction" stall cycles per issue.
@@ -98,9 +97,9 @@ void drop_events()
 // the lists into estimates.  Both work tile by tile (tile = grid nodes of one super block).
 struct SCfg {       // search kernel
     int warps;      // warps per CTA
-    int kcap;       // per-warp candidate list capacity (power of two)
     int cs;         // staged candidate capacity per CTA
-    int keepmax;    // max entries that survive a prune: noct>0 ? 8*noct : ndmax
+    int cap;        // entries per selection list: noct (octant search) or ndmax
+    int nlist;      // selection lists per node: 8 octants, or 1
     int pw_bytes;   // per-warp shared bytes
     int smem_bytes; // total dynamic shared bytes
 };
@@ -138,21 +137,30 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 // shared memory carve-up (bytes from the dynamic smem base)
 // search kernel
-//   CTA : [stage x,y,z f64 x cs][stage idx i32 x cs][chunk i32 x 3*threads]
-//   warp: [keys f64 x kcap][slots i32 x kcap]  candidate list
-//         [tau f64 x 8]                         per-octant bounds
-//         [hint i32 x 32]                       previous node's neighbours (slots)
-//         [octs u8 x kcap]                      octant of every listed candidate
-//         [sub u16 x cs/2]                      staged candidates that can matter to the walk
-__host__ __device__ inline int s_off_sidx(const SCfg &c) { return c.cs * 24; }
-__host__ __device__ inline int s_off_chunk(const SCfg &c) { return align16(s_off_sidx(c) + c.cs * 4); }
-__host__ __device__ inline int s_off_warp(const SCfg &c) { return align16(s_off_chunk(c) + c.warps * 32 * 12); }
-__host__ __device__ inline int spw_off_slots(const SCfg &c) { return c.kcap * 8; }
-__host__ __device__ inline int spw_off_tau(const SCfg &c) { return align16(spw_off_slots(c) + c.kcap * 4); }
-__host__ __device__ inline int spw_off_hint(const SCfg &c) { return spw_off_tau(c) + 64; }
-__host__ __device__ inline int spw_off_octs(const SCfg &c) { return spw_off_hint(c) + 128; }
-__host__ __device__ inline int spw_off_sub(const SCfg &c) { return spw_off_octs(c) + c.kcap; }
-__host__ __device__ inline int spw_bytes(const SCfg &c) { return align16(spw_off_sub(c) + (c.cs >> 1) * 2); }
+//   CTA : [stage x,y,z f64 x cs][stage sample index i32 x cs][stage bin u8 x cs]
+//         [run table i32 x 3*threads][bin histogram u16 x warps*SBINS][bin start u16 x SBINS+1]
+//         [reduction scratch f64 x 8*6]
+//   warp: [keys f64 x E*32][gidx i32 x E*32][tau f64 x nlist*32][meta u16 x nlist*32]
+//         E = nlist*cap entries per node, lane-interleaved: entry e of lane l at e*32 + l
+//   The staging temporaries (the candidates before the sort: sample index i32, rank u16,
+//   bin u8 each) overlay the per-warp regions, which are initialised afterwards.
+__host__ __device__ inline int s_off_sg(const SCfg &c) { return c.cs * 24; }
+__host__ __device__ inline int s_off_sbin(const SCfg &c) { return c.cs * 28; }
+__host__ __device__ inline int s_off_chunk(const SCfg &c) { return align16(c.cs * 29); }
+__host__ __device__ inline int s_off_whist(const SCfg &c) { return s_off_chunk(c) + c.warps * 32 * 12; }
+__host__ __device__ inline int s_off_bstart(const SCfg &c) { return s_off_whist(c) + c.warps * K3D_SBINS * 2; }
+__host__ __device__ inline int s_off_red(const SCfg &c) { return align16(s_off_bstart(c) + (K3D_SBINS + 1) * 2); }
+__host__ __device__ inline int s_off_warp(const SCfg &c) { return align16(s_off_red(c) + 8 * 6 * 8); }
+__host__ __device__ inline int spw_bytes(const SCfg &c)
+{
+    const int E = c.nlist * c.cap;
+    return align16(E * 384 + c.nlist * 256 + c.nlist * 64);
+}
+__host__ __device__ inline int s_total_bytes(const SCfg &c)
+{
+    const int lists = c.warps * spw_bytes(c), tmp = align16(7 * c.cs);
+    return s_off_warp(c) + (lists > tmp ? lists : tmp);
+}
 // solve kernel
 //   CTA : [tri LUT u16 x ntri][block points per structure f64 x 3*nst*ndb]
 //         [round table u16 x warps*rounds_per_warp]
@@ -512,35 +520,6 @@ __device__ __forceinline__ void smem_solve(double *Pm, const uint16_t *tri, int 
     est = -Pm[1];
 }
 
-__device__ __forceinline__ bool key_less(double ha, int sa, double hb, int sb)
-{
-    // distances are >= +0, so their bit patterns order like integers
-    long long ka = __double_as_longlong(ha), kb = __double_as_longlong(hb);
-    return (ka < kb) || (ka == kb && sa < sb);
-}
-
-// bitonic sort of (keys, slots)[0..n) ascending by (key, slot); n power of two >= 32
-__device__ __forceinline__ void warp_bitonic(double *keys, int *slots, int n, int lane)
-{
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = lane; t < (n >> 1); t += 32) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int l = i | j;
-                bool up = (i & k) == 0;
-                double ha = keys[i], hb = keys[l];
-                int sa = slots[i], sb = slots[l];
-                bool lt = key_less(hb, sb, ha, sa); // b < a
-                if (lt == up) {
-                    keys[i] = hb; keys[l] = ha;
-                    slots[i] = sb; slots[l] = sa;
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
 // sgsim.py:945-964 octant classification (repair D5); arguments are NODE - SAMPLE
 // (the sign the distance code already has), so every test is mirrored.
 __device__ __forceinline__ int octant_of_neg(double ndx, double ndy, double ndz)
@@ -560,203 +539,10 @@ __device__ __forceinline__ int octant_of_neg(double ndx, double ndy, double ndz)
     return iq;
 }
 
-struct NodeCtx {
-    double xloc, yloc, zloc;
-    const double *qx, *qy, *qz; // candidate coordinate arrays addressed by slot
-    int excl;                   // 1: samples at the location itself are not used (krige3d.py:359-363)
-};
-
 // krige3d.py:359-362: |dx| + |dy| + |dz| < eps (arguments: location - sample)
 __device__ __forceinline__ bool coincident(double ndx, double ndy, double ndz)
 {
     return __dadd_rn(__dadd_rn(fabs(ndx), fabs(ndy)), fabs(ndz)) < K3D_EPS;
-}
-
-// Sort the K collected candidates and keep what the reference would keep:
-// noct == 0 -> the ndmax nearest; noct > 0 -> per-octant nearest noct, at most 8*noct.
-__device__ __forceinline__ int prune_list(const K3dParams &P, const NodeCtx &nc, double *keys,
-                                          int *slots, int K, int lane, bool drop_self)
-{
-    if (K > 1) {
-        int n = 32;
-        while (n < K) n <<= 1;
-        for (int t = K + lane; t < n; t += 32) {
-            keys[t] = __longlong_as_double(0x7ff0000000000000LL);
-            slots[t] = 0x7fffffff;
-        }
-        __syncwarp();
-        warp_bitonic(keys, slots, n, lane);
-    }
-    if (P.noct <= 0)
-        return K < P.ndmax ? K : P.ndmax;
-    const unsigned lt = (1u << lane) - 1u;
-    const int nt = 8 * P.noct;
-    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int kept = 0;
-    for (int base = 0; base < K && kept < nt; base += 32) {
-        int j = base + lane;
-        bool valid = j < K;
-        int slot = valid ? slots[j] : 0;
-        double key = valid ? keys[j] : 0.0;
-        int iq = 8;
-        bool self = false;
-        if (valid) {
-            const double ndx = nc.xloc - nc.qx[slot], ndy = nc.yloc - nc.qy[slot],
-                         ndz = nc.zloc - nc.qz[slot];
-            iq = octant_of_neg(ndx, ndy, ndz);
-            self = drop_self && coincident(ndx, ndy, ndz);
-        }
-        int rank = 0;
-#pragma unroll
-        for (int o = 0; o < 8; o++) {
-            unsigned m = __ballot_sync(FULL, iq == o);
-            if (iq == o) rank = cnt[o] + __popc(m & lt);
-            cnt[o] += __popc(m);
-        }
-        // a sample at the location itself takes its place in the octant (the search does not
-        // know about it, super_block.py:185-224) and is dropped afterwards (krige3d.py:359)
-        bool keep = valid && rank < P.noct && !self;
-        unsigned km = __ballot_sync(FULL, keep);
-        __syncwarp();
-        if (keep) {
-            int pos = kept + __popc(km & lt);
-            keys[pos] = key;
-            slots[pos] = slot;
-        }
-        kept += __popc(km);
-        __syncwarp();
-    }
-    return kept;
-}
-
-// out-of-line copy for the rare mid-scan overflow (hot call sites inline prune_list so that
-// the list stays addressed as shared memory and the parameters as constants)
-__device__ __noinline__ int prune_list_cold(const K3dParams &P, const NodeCtx &nc, double *keys,
-                                            int *slots, int K, int lane, bool drop_self)
-{
-    return prune_list(P, nc, keys, slots, K, lane, drop_self);
-}
-
-// Selection for short lists (K <= 64, the usual case once the bounds of the previous node
-// apply): instead of sorting, the surplus is removed -- per octant the farthest candidates
-// beyond noct, then the farthest overall beyond ndmax -- one warp-wide lexicographic
-// maximum of (distance bits, slot) per removal.  Leaves the kept candidates, unordered,
-// at the front of the list; which ones are kept is exactly what the sort + octant pass keeps.
-__device__ __forceinline__ int select_small(const K3dParams &P, double *keys, int *slots,
-                                            const unsigned char *octs, int K, int lane)
-{   // octs[]: octant in bits 0-2; bit 7 = sample at the location itself (octant search of a
-    // cross-validation: it counts in its octant and is dropped afterwards)
-    const unsigned lt = (1u << lane) - 1u;
-    bool v0 = lane < K, v1 = lane + 32 < K;
-    const double k0 = v0 ? keys[lane] : 0.0, k1 = v1 ? keys[lane + 32] : 0.0;
-    const unsigned hi0 = (unsigned)__double2hiint(k0), lo0 = (unsigned)__double2loint(k0);
-    const unsigned hi1 = (unsigned)__double2hiint(k1), lo1 = (unsigned)__double2loint(k1);
-    const int s0 = v0 ? slots[lane] : 0, s1 = v1 ? slots[lane + 32] : 0;
-    const int f0 = v0 ? octs[lane] : 8, f1 = v1 ? octs[lane + 32] : 8;
-    const int o0 = f0 & 15, o1 = f1 & 15;
-    // removes the lexicographically largest element among those flagged a0 / a1
-    auto remove_max = [&](bool a0, bool a1) {
-        const bool use1 = a1 && (!a0 || hi1 > hi0 || (hi1 == hi0 && (lo1 > lo0 || (lo1 == lo0 && s1 > s0))));
-        const bool any = a0 || a1;
-        const unsigned ch = any ? (use1 ? hi1 : hi0) : 0u;
-        const unsigned mh = __reduce_max_sync(FULL, ch);
-        bool mine = any && ch == mh;
-        if (__popc(__ballot_sync(FULL, mine)) > 1) { // equal high words (rare): low word, then slot
-            const unsigned cl = mine ? (use1 ? lo1 : lo0) : 0u;
-            const unsigned ml = __reduce_max_sync(FULL, cl);
-            mine = mine && cl == ml;
-            if (__popc(__ballot_sync(FULL, mine)) > 1) {
-                const unsigned cs = mine ? (unsigned)(use1 ? s1 : s0) + 1u : 0u;
-                const unsigned ms = __reduce_max_sync(FULL, cs);
-                mine = mine && cs == ms;
-            }
-        }
-        if (mine) {
-            if (use1) v1 = false; else v0 = false;
-        }
-    };
-    if (P.noct > 0) {
-        for (int o = 0; o < 8; o++) {
-            int c = __popc(__ballot_sync(FULL, v0 && o0 == o)) + __popc(__ballot_sync(FULL, v1 && o1 == o));
-            for (; c > P.noct; c--) remove_max(v0 && o0 == o, v1 && o1 == o);
-        }
-        v0 = v0 && !(f0 & 0x80);
-        v1 = v1 && !(f1 & 0x80);
-    }
-    int total = __popc(__ballot_sync(FULL, v0)) + __popc(__ballot_sync(FULL, v1));
-    for (; total > P.ndmax; total--) remove_max(v0, v1);
-    // compact the survivors to the front (all lanes hold their elements in registers)
-    const unsigned m0 = __ballot_sync(FULL, v0), m1 = __ballot_sync(FULL, v1);
-    __syncwarp();
-    if (v0) { const int p = __popc(m0 & lt); keys[p] = k0; slots[p] = s0; }
-    if (v1) { const int p = __popc(m0) + __popc(m1 & lt); keys[p] = k1; slots[p] = s1; }
-    __syncwarp();
-    return total;
-}
-
-// Scan `count` contiguous candidates (slots slot0..slot0+count) and append those within
-// the search radius -- and within the caller's exact per-octant upper bounds tau[] --
-// to the warp's list; prunes when the list could overflow.
-__device__ __forceinline__ int scan_candidates(const K3dParams &P, const int kcap,
-                                               const NodeCtx &nc, int slot0, int count,
-                                               const double *tau, double *keys, int *slots,
-                                               unsigned char *octs, int K, int lane,
-                                               const unsigned short *sub = nullptr)
-{
-    const double *rs = P.rotmat + 9 * P.nst;
-    const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < count; base += 32) {
-        int c = base + lane;
-        bool in = false;
-        double h = 0.0;
-        int oq = 0, s = 0;
-        if (c < count) {
-            s = sub ? (int)sub[c] : slot0 + c; // candidates come from the walk's short list
-            // point1 = node, point2 = sample (super_block.py:301-305)
-            double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
-                   dz = __dsub_rn(nc.zloc, nc.qz[s]);
-            h = sqdist_exact(dx, dy, dz, rs);
-            // reference: `if hsqd > radsqd: continue`; tau[] <= radsqd are exact upper
-            // bounds of what can still be selected in the sample's octant
-            oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
-            in = !(h > tau[oq & 7]);
-            if (nc.excl && coincident(dx, dy, dz)) { // krige3d.py:359-363
-                if (P.noct > 0) oq |= 0x80; // still takes its place in the octant
-                else in = false;
-            }
-        }
-        unsigned m = __ballot_sync(FULL, in);
-        if (m == 0u)
-            continue;
-        if (K + 32 > kcap) { // rare: thin the list (sorted afterwards); re-derive octants
-            __syncwarp();
-            K = prune_list_cold(P, nc, keys, slots, K, lane, false); // keeps a sample at the location
-            for (int t = lane; t < K; t += 32) {
-                const int sl = slots[t];
-                const double ndx = nc.xloc - nc.qx[sl], ndy = nc.yloc - nc.qy[sl], ndz = nc.zloc - nc.qz[sl];
-                int oq2 = P.noct > 0 ? octant_of_neg(ndx, ndy, ndz) : 0;
-                if (P.noct > 0 && nc.excl && coincident(ndx, ndy, ndz)) oq2 |= 0x80;
-                octs[t] = (unsigned char)oq2;
-            }
-            __syncwarp();
-        }
-        if (in) {
-            int pos = K + __popc(m & lt);
-            keys[pos] = h;
-            slots[pos] = s;
-            octs[pos] = (unsigned char)oq;
-        }
-        K += __popc(m);
-    }
-    return K;
-}
-// out-of-line copy for the global-memory fallback walk
-__device__ __noinline__ int scan_candidates_cold(const K3dParams &P, const int kcap,
-                                                 const NodeCtx &nc, int slot0, int count,
-                                                 const double *tau, double *keys, int *slots,
-                                                 unsigned char *octs, int K, int lane)
-{
-    return scan_candidates(P, kcap, nc, slot0, count, tau, keys, slots, octs, K, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -779,11 +565,14 @@ struct PtSet {
     int exclude;
 };
 
+// (the grid covers the tiles tile0 .. tile0 + gridDim.x - 1: the super-block layers that can
+// meet the slab)
 __device__ __forceinline__ Tile tile_of_block(const K3dParams &P, const K3dInputs &in, int iz0,
-                                              int iz1, const PtSet &pts)
+                                              int iz1, const PtSet &pts, int tile0)
 {
     Tile T;
-    int tile = blockIdx.x;
+    int tile = blockIdx.x + tile0;
+    const int tile_id = tile;
     T.sbx = tile % P.nxsup;
     tile /= P.nxsup;
     T.sby = tile % P.nysup;
@@ -793,8 +582,8 @@ __device__ __forceinline__ Tile tile_of_block(const K3dParams &P, const K3dInput
     T.zsb0 = in.nodez0[T.sbz];
     T.first = 0;
     if (pts.x) { // the tile's "nodes" are the locations listed for this super block
-        T.first = pts.start[blockIdx.x];
-        T.tnodes = pts.start[blockIdx.x + 1] - T.first;
+        T.first = pts.start[tile_id];
+        T.tnodes = pts.start[tile_id + 1] - T.first;
         T.z0 = T.zsb0;
         T.tnx = T.tny = T.tnz = 1;
         return T;
@@ -851,296 +640,415 @@ __device__ __forceinline__ void snake_node(const Tile &T, int t, int &lx, int &l
 //                                 by (distance, index) and -1 padded when `ordered`
 //   cnt[node - slab]              number of neighbours, min(nclose, ndmax)
 // ---------------------------------------------------------------------------
+// One CTA per tile, ONE THREAD PER NODE.  All nodes of a tile search the same super blocks,
+// so the candidate samples are gathered once per CTA -- and ordered by their distance from
+// the centre of the tile (64 bins in squared distance, a stable counting sort).  A thread
+// then streams the candidates in that order (every lane of a warp reads the same candidate:
+// shared-memory broadcasts), evaluates the reference's distance exactly as it does
+// (sqdist_exact) and keeps, per octant, the `noct` nearest seen so far (or the `ndmax`
+// nearest overall) in a small lane-interleaved list with its farthest entry tracked.
+// Because the stream arrives nearest-first, the lists converge early, and the thread stops
+// as soon as the triangle inequality rules out everything that is left:
+//     sqrt(h(centre, s)) - sqrt(h(centre, node)) > sqrt(max over lists of the farthest kept)
+// Exactness: which samples are kept is decided on the reference's own distance values with
+// ties broken by sample index, the order of the stream only decides when the thread may
+// stop; the bound is applied with a 1e-9 safety margin on the safe side.
 // PTS: estimation at listed locations (K3dPoints) instead of grid nodes -- a separate
-// instantiation, so that the grid kernel carries none of the coincident-sample logic
-template <bool PTS>
-__global__ void __launch_bounds__(256, 4)
+// instantiation, so that the grid kernel carries none of the coincident-sample logic.
+// OCT: octant search (noct > 0).
+template <bool PTS, bool OCT>
+__global__ void __launch_bounds__(256)
 k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const int iz0,
-                  const int iz1, int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
-                  int32_t *__restrict__ ncand_out, const int ordered,
+                  const int iz1, const int tile0, int32_t *__restrict__ nbr,
+                  int32_t *__restrict__ cnt, int32_t *__restrict__ ncand_out, const int ordered,
                   const __grid_constant__ SCfg cfg, const __grid_constant__ PtSet pts)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthreads = cfg.warps * 32;
+    const int NT = cfg.warps * 32;
 
     double *stx = (double *)smem;
     double *sty = stx + cfg.cs;
     double *stz = sty + cfg.cs;
-    int *stidx = (int *)(smem + s_off_sidx(cfg));
-    int *chunk = (int *)(smem + s_off_chunk(cfg)); // [3][nthreads]: lo, cnt, off
-    unsigned char *wbase = smem + s_off_warp(cfg) + warp * spw_bytes(cfg);
-    double *keys = (double *)wbase;
-    int *slots = (int *)(wbase + spw_off_slots(cfg));
-    double *tau = (double *)(wbase + spw_off_tau(cfg));
-    int *hint = (int *)(wbase + spw_off_hint(cfg));
-    unsigned char *octs = wbase + spw_off_octs(cfg);
-    unsigned short *sub = (unsigned short *)(wbase + spw_off_sub(cfg));
+    int *stg = (int *)(smem + s_off_sg(cfg));
+    unsigned char *sbin = smem + s_off_sbin(cfg);
+    int *chunk = (int *)(smem + s_off_chunk(cfg)); // [3][NT]: lo, cnt, off of a batch of runs
+    unsigned short *whist = (unsigned short *)(smem + s_off_whist(cfg));
+    unsigned short *bstart = (unsigned short *)(smem + s_off_bstart(cfg));
+    double *red = (double *)(smem + s_off_red(cfg));
+    unsigned char *wreg = smem + s_off_warp(cfg);
+    // staging temporaries (the candidates before the sort) overlay the per-warp regions
+    int *gtmp = (int *)wreg;
+    unsigned short *rtmp = (unsigned short *)(wreg + 4 * cfg.cs);
+    unsigned char *btmp = wreg + 6 * cfg.cs;
 
-    __shared__ int s_total, s_warpsum[32];
+    __shared__ int s_warpsum[8];
 
     const PtSet nopts = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     const PtSet &geo = PTS ? pts : nopts; // (folds to grid mode at compile time)
-    const Tile T = tile_of_block(P, in, iz0, iz1, geo);
+    const Tile T = tile_of_block(P, in, iz0, iz1, geo, tile0);
     if (T.tnodes <= 0)
         return;
     const int sbx = T.sbx, sby = T.sby, sbz = T.sbz;
-
-    // ---- stage the candidate samples of this tile (ascending sorted index) ---
-    bool staged = true;
-    {
-        int total = 0;
-        for (int r0 = 0; r0 < in.nruns; r0 += nthreads) {
-            int r = r0 + tid;
-            int lo = 0, n = 0;
-            if (r < in.nruns) {
-                const int16_t *rn = in.runs + 4 * r;
-                int by = sby + rn[2], bz = sbz + rn[3];
-                if (by >= 0 && by < P.nysup && bz >= 0 && bz < P.nzsup) {
-                    int bx0 = sbx + rn[0], bx1 = sbx + rn[1];
-                    bx0 = bx0 < 0 ? 0 : bx0;
-                    bx1 = bx1 >= P.nxsup ? P.nxsup - 1 : bx1;
-                    if (bx0 <= bx1) {
-                        int b = (bz * P.nysup + by) * P.nxsup;
-                        lo = in.sbstart[b + bx0];
-                        n = in.sbstart[b + bx1 + 1] - lo;
-                    }
-                }
-            }
-            int incl = n; // CTA-wide exclusive scan of n
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int v = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += v;
-            }
-            if (lane == 31) s_warpsum[warp] = incl;
-            __syncthreads();
-            int woff = 0, ctot = 0;
-            for (int w = 0; w < cfg.warps; w++) {
-                int v = s_warpsum[w];
-                if (w < warp) woff += v;
-                ctot += v;
-            }
-            chunk[tid] = lo;
-            chunk[nthreads + tid] = n;
-            chunk[2 * nthreads + tid] = total + woff + incl - n;
-            total += ctot;
-            __syncthreads();
-            if (total <= cfg.cs) {
-                int nr = in.nruns - r0;
-                nr = nr < nthreads ? nr : nthreads;
-                for (int q = warp; q < nr; q += cfg.warps) {
-                    int qlo = chunk[q], qcnt = chunk[nthreads + q], qoff = chunk[2 * nthreads + q];
-                    for (int i = lane; i < qcnt; i += 32) {
-                        stx[qoff + i] = in.sx[qlo + i];
-                        sty[qoff + i] = in.sy[qlo + i];
-                        stz[qoff + i] = in.sz[qlo + i];
-                        stidx[qoff + i] = qlo + i;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        if (tid == 0) s_total = total;
-        __syncthreads();
-        staged = s_total <= cfg.cs;
-    }
-    const int ncand = s_total;
-    const size_t slab_off = (size_t)iz0 * P.nx * P.ny;
     const unsigned ltm = (1u << lane) - 1u;
+    const double *rs = P.rotmat + 9 * P.nst;
 
-    NodeCtx nc;
-    nc.qx = staged ? stx : in.sx;
-    nc.qy = staged ? sty : in.sy;
-    nc.qz = staged ? stz : in.sz;
-    nc.excl = PTS ? pts.exclude : 0;
-
-    // ---- each warp walks a contiguous piece of a boustrophedon path through the tile:
-    //      consecutive nodes are grid neighbours, so their neighbourhoods overlap ---------
-    const int per = (T.tnodes + cfg.warps - 1) / cfg.warps;
-    const int t_begin = warp * per, t_end = (t_begin + per < T.tnodes) ? t_begin + per : T.tnodes;
-    int nhint = -1; // previous node's neighbours listed in hint[]
-
-    // ---- candidates that can matter to this walk ------------------------------------------
-    // A sample farther from the centre of the walk's bounding box than radius + rho (rho =
-    // the box's half diagonal in the search metric) is out of range of every node of the
-    // walk (triangle inequality), so the per-node scans only visit the others.
-    int nsubw = -1; // length of sub[], or -1: scan every staged candidate
-    if (staged && t_begin < t_end) {
-        double bcx, bcy, bcz, ex, ey, ez; // centre and half extents of the walk's bounding box
-        if (PTS) {
-            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-            for (int t = t_begin + lane; t < t_end; t += 32) {
-                const size_t q = (size_t)(T.first + t);
-                lo[0] = fmin(lo[0], pts.x[q]); hi[0] = fmax(hi[0], pts.x[q]);
-                lo[1] = fmin(lo[1], pts.y[q]); hi[1] = fmax(hi[1], pts.y[q]);
-                lo[2] = fmin(lo[2], pts.z[q]); hi[2] = fmax(hi[2], pts.z[q]);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    lo[k] = fmin(lo[k], __shfl_xor_sync(FULL, lo[k], d));
-                    hi[k] = fmax(hi[k], __shfl_xor_sync(FULL, hi[k], d));
+    // ---- 1. the tile's candidates: template runs clipped to the grid, ascending index ----
+    int total = 0;
+    for (int r0 = 0; r0 < in.nruns; r0 += NT) {
+        const int r = r0 + tid;
+        int lo = 0, n = 0;
+        if (r < in.nruns) {
+            const int16_t *rn = in.runs + 4 * r;
+            const int by = sby + rn[2], bz = sbz + rn[3];
+            if (by >= 0 && by < P.nysup && bz >= 0 && bz < P.nzsup) {
+                int bx0 = sbx + rn[0], bx1 = sbx + rn[1];
+                bx0 = bx0 < 0 ? 0 : bx0;
+                bx1 = bx1 >= P.nxsup ? P.nxsup - 1 : bx1;
+                if (bx0 <= bx1) {
+                    const int b = (bz * P.nysup + by) * P.nxsup;
+                    lo = in.sbstart[b + bx0];
+                    n = in.sbstart[b + bx1 + 1] - lo;
                 }
-            bcx = 0.5 * (lo[0] + hi[0]); bcy = 0.5 * (lo[1] + hi[1]); bcz = 0.5 * (lo[2] + hi[2]);
-            // (the 1e-9 margin on `reach` below also covers the rounding of these halves)
-            ex = 0.5 * (hi[0] - lo[0]); ey = 0.5 * (hi[1] - lo[1]); ez = 0.5 * (hi[2] - lo[2]);
-        } else {
-            int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
-            for (int t = t_begin + lane; t < t_end; t += 32) {
-                int lx, ly, lz;
-                snake_node(T, t, lx, ly, lz);
-                lo[0] = min(lo[0], lx); hi[0] = max(hi[0], lx);
-                lo[1] = min(lo[1], ly); hi[1] = max(hi[1], ly);
-                lo[2] = min(lo[2], lz); hi[2] = max(hi[2], lz);
             }
+        }
+        int incl = n; // CTA-wide exclusive scan of n
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warpsum[warp] = incl;
+        __syncthreads();
+        int woff = 0, ctot = 0;
+        for (int w = 0; w < cfg.warps; w++) {
+            const int v = s_warpsum[w];
+            if (w < warp) woff += v;
+            ctot += v;
+        }
+        chunk[tid] = lo;
+        chunk[NT + tid] = n;
+        chunk[2 * NT + tid] = total + woff + incl - n;
+        total += ctot;
+        __syncthreads();
+        if (total <= cfg.cs) {
+            int nr = in.nruns - r0;
+            nr = nr < NT ? nr : NT;
+            for (int q = warp; q < nr; q += cfg.warps) {
+                const int qlo = chunk[q], qcnt = chunk[NT + q], qoff = chunk[2 * NT + q];
+                for (int i = lane; i < qcnt; i += 32) gtmp[qoff + i] = qlo + i;
+            }
+        }
+        __syncthreads();
+    }
+    const bool staged = total <= cfg.cs; // else: every thread walks the runs in global memory
+
+    // ---- 2. centre of the tile's nodes and their largest distance from it ------------------
+    double cx, cy, cz, ex, ey, ez;
+    if (PTS) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int t = tid; t < T.tnodes; t += NT) {
+            const size_t q = (size_t)(T.first + t);
+            lo[0] = fmin(lo[0], pts.x[q]); hi[0] = fmax(hi[0], pts.x[q]);
+            lo[1] = fmin(lo[1], pts.y[q]); hi[1] = fmax(hi[1], pts.y[q]);
+            lo[2] = fmin(lo[2], pts.z[q]); hi[2] = fmax(hi[2], pts.z[q]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                lo[k] = fmin(lo[k], __shfl_xor_sync(FULL, lo[k], d));
+                hi[k] = fmax(hi[k], __shfl_xor_sync(FULL, hi[k], d));
+            }
+            if (lane == 0) { red[warp * 6 + k] = lo[k]; red[warp * 6 + 3 + k] = hi[k]; }
+        }
+        __syncthreads();
+        for (int w = 0; w < cfg.warps; w++)
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                lo[k] = __reduce_min_sync(FULL, lo[k]);
-                hi[k] = __reduce_max_sync(FULL, hi[k]);
+                lo[k] = fmin(lo[k], red[w * 6 + k]);
+                hi[k] = fmax(hi[k], red[w * 6 + 3 + k]);
             }
-            bcx = P.xmn + (T.x0 + 0.5 * (lo[0] + hi[0])) * P.xsiz;
-            bcy = P.ymn + (T.y0 + 0.5 * (lo[1] + hi[1])) * P.ysiz;
-            bcz = P.zmn + (T.z0 + 0.5 * (lo[2] + hi[2])) * P.zsiz;
-            ex = 0.5 * (hi[0] - lo[0]) * fabs(P.xsiz); ey = 0.5 * (hi[1] - lo[1]) * fabs(P.ysiz);
-            ez = 0.5 * (hi[2] - lo[2]) * fabs(P.zsiz);
-        }
-        const double *rs = P.rotmat + 9 * P.nst;
-        double rho2 = 0.0; // corners come in +- pairs: four sign patterns suffice
-        rho2 = fmax(rho2, sqdist_exact(ex, ey, ez, rs));
-        rho2 = fmax(rho2, sqdist_exact(ex, ey, -ez, rs));
-        rho2 = fmax(rho2, sqdist_exact(ex, -ey, ez, rs));
-        rho2 = fmax(rho2, sqdist_exact(ex, -ey, -ez, rs));
-        const double reach = (sqrt(P.radsqd) + sqrt(rho2)) * (1.0 + 1e-9);
-        const double reach2 = reach * reach;
-        const int subcap = cfg.cs >> 1;
-        int n = 0;
-        for (int base = 0; base < ncand; base += 32) {
-            const int c = base + lane;
-            bool near = false;
-            if (c < ncand) near = !(sqdist_exact(bcx - stx[c], bcy - sty[c], bcz - stz[c], rs) > reach2);
-            const unsigned m = __ballot_sync(FULL, near);
-            if (n + 32 > subcap) { n = -1; break; } // does not fit: keep the full scan
-            if (near) sub[n + __popc(m & ltm)] = (unsigned short)c;
-            n += __popc(m);
-        }
-        nsubw = n;
-        __syncwarp();
+        cx = 0.5 * (lo[0] + hi[0]); cy = 0.5 * (lo[1] + hi[1]); cz = 0.5 * (lo[2] + hi[2]);
+        // (the 1e-9 margins below also cover the rounding of these halves)
+        ex = 0.5 * (hi[0] - lo[0]); ey = 0.5 * (hi[1] - lo[1]); ez = 0.5 * (hi[2] - lo[2]);
+    } else {
+        cx = P.xmn + (T.x0 + 0.5 * (T.tnx - 1)) * P.xsiz;
+        cy = P.ymn + (T.y0 + 0.5 * (T.tny - 1)) * P.ysiz;
+        cz = P.zmn + (T.z0 + 0.5 * (T.tnz - 1)) * P.zsiz;
+        ex = 0.5 * (T.tnx - 1) * fabs(P.xsiz); ey = 0.5 * (T.tny - 1) * fabs(P.ysiz);
+        ez = 0.5 * (T.tnz - 1) * fabs(P.zsiz);
     }
+    double rho2 = sqdist_exact(ex, ey, ez, rs); // corners come in +- pairs: four sign patterns
+    rho2 = fmax(rho2, sqdist_exact(ex, ey, -ez, rs));
+    rho2 = fmax(rho2, sqdist_exact(ex, -ey, ez, rs));
+    rho2 = fmax(rho2, sqdist_exact(ex, -ey, -ez, rs));
+    // no node of the tile can reach a sample farther from the centre than this
+    const double reach = (sqrt(P.radsqd) + sqrt(rho2)) * (1.0 + 1e-9);
+    const double hcmax = reach * reach;
+    const double bscale = (double)K3D_SBINS / hcmax;
+    const double binw = hcmax / (double)K3D_SBINS * (1.0 - 1e-12); // bin b starts at >= b * binw
 
-    for (int t = t_begin; t < t_end; t++) {
-        const NodeLoc L = node_of_tile(P, T, geo, t, slab_off);
-        const size_t o = L.o;
-        nc.xloc = L.x; nc.yloc = L.y; nc.zloc = L.z;
-        int tested = 0;
-
-        // ---- 0. exact upper bounds from the previous node's neighbours ----------------
-        // Any set of samples bounds the selection: once `need` of them (noct per octant, or
-        // ndmax overall) are seen within the radius in an octant, nothing farther than the
-        // farthest of those can be selected there.
-        {
-            double mytau = P.radsqd;
-            if (nhint > 0) {
-                const double *rs = P.rotmat + 9 * P.nst;
-                const int noctants = P.noct > 0 ? 8 : 1;
-                const int need = P.noct > 0 ? P.noct : P.ndmax;
-                int cq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                unsigned bh = 0, bl = 0; // lane q: running max of octant q's first `need`
-                for (int h0 = 0; h0 < nhint; h0 += 32) {
-                    bool inr = false;
-                    int oq = 0;
-                    unsigned hi = 0, lo = 0;
-                    if (h0 + lane < nhint) {
-                        const int s = hint[h0 + lane];
-                        double dx = __dsub_rn(nc.xloc, nc.qx[s]), dy = __dsub_rn(nc.yloc, nc.qy[s]),
-                               dz = __dsub_rn(nc.zloc, nc.qz[s]);
-                        double h = sqdist_exact(dx, dy, dz, rs);
-                        inr = !(h > P.radsqd);
-                        // without octants a sample at the location itself is never a candidate
-                        if (nc.excl && P.noct <= 0 && coincident(dx, dy, dz)) inr = false;
-                        oq = P.noct > 0 ? octant_of_neg(dx, dy, dz) : 0;
-                        hi = (unsigned)__double2hiint(h);
-                        lo = (unsigned)__double2loint(h);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (q < noctants) {
-                            const unsigned mq = __ballot_sync(FULL, inr && oq == q);
-                            const bool mine = inr && oq == q && cq[q] + __popc(mq & ltm) < need;
-                            cq[q] += __popc(mq);
-                            const unsigned mh = __reduce_max_sync(FULL, mine ? hi : 0u);
-                            const unsigned ml = __reduce_max_sync(FULL, (mine && hi == mh) ? lo : 0u);
-                            if (lane == q && (mh > bh || (mh == bh && ml > bl))) { bh = mh; bl = ml; }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if (lane == q && cq[q] >= need) mytau = __hiloint2double((int)bh, (int)bl);
+    // ---- 3. order the candidates by distance from the centre (stable counting sort) -------
+    // Warp w bins a contiguous piece of the candidate list, 32 at a time in list order; a
+    // candidate's place is (bin, warp, round, lane), which is its place in a stable sort.
+    if (staged) {
+        const int per_w = ((total + NT - 1) / NT) * 32;
+        const int wbeg = min(total, warp * per_w), wend = min(total, wbeg + per_w);
+        for (int b = lane; b < K3D_SBINS; b += 32) whist[warp * K3D_SBINS + b] = 0;
+        __syncwarp();
+        for (int i0 = wbeg; i0 < wend; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < wend;
+            int bin = 255; // not a candidate of any node of the tile
+            if (valid) {
+                const int g = gtmp[i];
+                const double hc = sqdist_exact(cx - in.sx[g], cy - in.sy[g], cz - in.sz[g], rs);
+                if (!(hc > hcmax)) bin = min(K3D_SBINS - 1, (int)(hc * bscale));
             }
-            if (lane < 8) tau[lane] = mytau;
+            const unsigned peers = __match_any_sync(FULL, bin);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (bin != 255 && lane == leader) {
+                base = whist[warp * K3D_SBINS + bin];
+                whist[warp * K3D_SBINS + bin] = (unsigned short)(base + __popc(peers));
+            }
+            base = __shfl_sync(FULL, base, leader);
+            if (valid) {
+                btmp[i] = (unsigned char)bin;
+                rtmp[i] = (unsigned short)(base + __popc(peers & ltm));
+            }
             __syncwarp();
         }
+        __syncthreads();
+        for (int b = tid; b < K3D_SBINS; b += NT) { // exclusive prefix over the warps of a bin
+            int run = 0;
+            for (int w = 0; w < cfg.warps; w++) {
+                const int v = whist[w * K3D_SBINS + b];
+                whist[w * K3D_SBINS + b] = (unsigned short)run;
+                run += v;
+            }
+            bstart[b] = (unsigned short)run;
+        }
+        __syncthreads();
+        if (warp == 0) { // exclusive prefix over the bins, two per lane
+            const int a = bstart[2 * lane], b2 = bstart[2 * lane + 1];
+            int incl = a + b2;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += v;
+            }
+            __syncwarp();
+            bstart[2 * lane] = (unsigned short)(incl - a - b2);
+            bstart[2 * lane + 1] = (unsigned short)(incl - b2);
+            if (lane == 31) bstart[K3D_SBINS] = (unsigned short)incl;
+        }
+        __syncthreads();
+        for (int i0 = wbeg; i0 < wend; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < wend) {
+                const int bin = btmp[i];
+                if (bin != 255) {
+                    const int pos = bstart[bin] + whist[warp * K3D_SBINS + bin] + rtmp[i];
+                    const int g = gtmp[i];
+                    stx[pos] = in.sx[g];
+                    sty[pos] = in.sy[g];
+                    stz[pos] = in.sz[g];
+                    stg[pos] = g;
+                    sbin[pos] = (unsigned char)bin;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int nsorted = staged ? (int)bstart[K3D_SBINS] : 0;
 
-        // ---- 1. scan ---------------------------------------------------------------------
-        int K = 0;
-        if (staged) {
-            NodeCtx ns = nc; // staged coordinates: plain shared-memory pointers
-            ns.qx = stx; ns.qy = sty; ns.qz = stz;
-            if (nsubw >= 0) {
-                tested = nsubw;
-                K = scan_candidates(P, cfg.kcap, ns, 0, nsubw, tau, keys, slots, octs, K, lane, sub);
+    // ---- 4. one thread per node: stream the candidates, keep the nearest ------------------
+    const int cap = cfg.cap, nlist = OCT ? 8 : 1, E = nlist * cap;
+    double *keys = (double *)(wreg + warp * cfg.pw_bytes); // [E][32] distances
+    int *gidx = (int *)((unsigned char *)keys + E * 256);  // [E][32] sample index (bit 31: the
+                                                           //  sample at the location itself)
+    double *tau = (double *)((unsigned char *)keys + E * 384);          // [nlist][32] farthest kept
+    unsigned short *meta = (unsigned short *)((unsigned char *)tau + nlist * 256); // count | argmax << 8
+    unsigned *outl = (unsigned *)keys; // [ndmax][33] output staging, once the keys are dead
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const unsigned GM = 0x7fffffffu;
+    const size_t slab_off = (size_t)iz0 * P.nx * P.ny;
+    const int excl = PTS ? pts.exclude : 0;
+
+    for (int base = warp * 32; base < T.tnodes; base += NT) {
+        const int t = base + lane;
+        const bool active = t < T.tnodes;
+        double xloc = 0.0, yloc = 0.0, zloc = 0.0;
+        size_t o = 0;
+        if (active) {
+            if (PTS) {
+                o = (size_t)(T.first + t);
+                xloc = pts.x[o]; yloc = pts.y[o]; zloc = pts.z[o];
             } else {
-                tested = ncand;
-                K = scan_candidates(P, cfg.kcap, ns, 0, ncand, tau, keys, slots, octs, K, lane);
+                const int lx = t % T.tnx, q = t / T.tnx;
+                const int ly = q % T.tny, lz = q / T.tny;
+                const int ix = T.x0 + lx, iy = T.y0 + ly, iz = T.z0 + lz;
+                o = (((size_t)iz * P.ny + iy) * P.nx + ix) - slab_off;
+                // krige3d.py:307-309: xmn + ix*xsiz, multiply then add, unfused
+                xloc = __dadd_rn(P.xmn, __dmul_rn((double)ix, P.xsiz));
+                yloc = __dadd_rn(P.ymn, __dmul_rn((double)iy, P.ysiz));
+                zloc = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
+            }
+        }
+        for (int l = 0; l < nlist; l++) {
+            tau[l * 32 + lane] = INF; // a list that is not full accepts anything in the radius
+            meta[l * 32 + lane] = 0;
+        }
+        const double rho = sqrt(sqdist_exact(xloc - cx, yloc - cy, zloc - cz, rs));
+        // candidates whose squared distance from the centre exceeds `limit` cannot be kept
+        auto limit_of = [&](double tmax) {
+            const double s = sqrt(fmin(tmax, P.radsqd)) + rho;
+            return s * s * (1.0 + 1e-9);
+        };
+        double limit = limit_of(INF);
+        bool done = !active, changed = false;
+        int tested = 0;
+
+        auto consider = [&](double sx_, double sy_, double sz_, int g) {
+            // point1 = node, point2 = sample (super_block.py:301-305)
+            const double dx = __dsub_rn(xloc, sx_), dy = __dsub_rn(yloc, sy_), dz = __dsub_rn(zloc, sz_);
+            const double h = sqdist_exact(dx, dy, dz, rs);
+            if (h > P.radsqd) return; // super_block.py:306
+            int l = 0;
+            unsigned gf = (unsigned)g;
+            if (OCT) l = octant_of_neg(dx, dy, dz);
+            if (PTS && excl && coincident(dx, dy, dz)) { // krige3d.py:359-363
+                if (!OCT) return;      // never a candidate
+                gf |= ~GM;             // takes its place in the octant, dropped afterwards
+            }
+            const double tl = tau[l * 32 + lane];
+            if (h > tl) return;
+            const int m = meta[l * 32 + lane];
+            int n = m & 255;
+            const int im = m >> 8, row0 = l * cap;
+            if (n == cap) { // full: it must beat the farthest kept, (tl, index) lexicographically
+                if (h == tl && (gf & GM) > ((unsigned)gidx[(row0 + im) * 32 + lane] & GM)) return;
+                keys[(row0 + im) * 32 + lane] = h;
+                gidx[(row0 + im) * 32 + lane] = (int)gf;
+            } else {
+                keys[(row0 + n) * 32 + lane] = h;
+                gidx[(row0 + n) * 32 + lane] = (int)gf;
+                n++;
+                if (n < cap) {
+                    meta[l * 32 + lane] = (unsigned short)(n | (im << 8));
+                    return;
+                }
+            }
+            // the list is full: its farthest entry, largest (distance, index), is the new bound
+            int bi = 0;
+            double bk = keys[row0 * 32 + lane];
+            for (int e = 1; e < cap; e++) {
+                const double k = keys[(row0 + e) * 32 + lane];
+                bool gt = k > bk;
+                if (k == bk)
+                    gt = ((unsigned)gidx[(row0 + e) * 32 + lane] & GM) > ((unsigned)gidx[(row0 + bi) * 32 + lane] & GM);
+                if (gt) { bk = k; bi = e; }
+            }
+            tau[l * 32 + lane] = bk;
+            meta[l * 32 + lane] = (unsigned short)(cap | (bi << 8));
+            changed = true;
+        };
+
+        if (staged) {
+            for (int c0 = 0; c0 < nsorted; c0 += K3D_SCHUNK) {
+                if (!done) {
+                    if (changed) { // a bound moved: what is the farthest anything can still be?
+                        double tmax = tau[lane];
+                        for (int l = 1; l < nlist; l++) tmax = fmax(tmax, tau[l * 32 + lane]);
+                        limit = limit_of(tmax);
+                        changed = false;
+                    }
+                    done = (double)sbin[c0] * binw > limit;
+                }
+                if (__all_sync(FULL, done)) break;
+                if (!done) {
+                    const int c1 = min(c0 + K3D_SCHUNK, nsorted);
+                    for (int c = c0; c < c1; c++) consider(stx[c], sty[c], stz[c], stg[c]);
+                    tested += c1 - c0;
+                }
             }
         } else { // tile too dense for the stage: walk the runs in global memory
             for (int r = 0; r < in.nruns; r++) {
                 const int16_t *rn = in.runs + 4 * r;
-                int by = sby + rn[2], bz = sbz + rn[3];
+                const int by = sby + rn[2], bz = sbz + rn[3];
                 if (by < 0 || by >= P.nysup || bz < 0 || bz >= P.nzsup) continue;
                 int bx0 = sbx + rn[0], bx1 = sbx + rn[1];
                 bx0 = bx0 < 0 ? 0 : bx0;
                 bx1 = bx1 >= P.nxsup ? P.nxsup - 1 : bx1;
                 if (bx0 > bx1) continue;
-                int b = (bz * P.nysup + by) * P.nxsup;
-                int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
-                K = scan_candidates_cold(P, cfg.kcap, nc, lo, hi - lo, tau, keys, slots, octs, K, lane);
+                const int b = (bz * P.nysup + by) * P.nxsup;
+                const int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
+                if (active)
+                    for (int i = lo; i < hi; i++) consider(in.sx[i], in.sy[i], in.sz[i], i);
                 tested += hi - lo;
             }
         }
-        __syncwarp();
-        // ---- 2. select: which candidates the reference keeps (super_block.py:313-316 + octants)
-        if (K <= 64) {
-            K = select_small(P, keys, slots, octs, K, lane);
-            if (ordered && K > 1) { // reported lists are ordered by (distance, index)
-                const int n = K <= 32 ? 32 : 64;
-                for (int e = K + lane; e < n; e += 32) {
-                    keys[e] = __longlong_as_double(0x7ff0000000000000LL);
-                    slots[e] = 0x7fffffff;
+
+        // ---- 5. what the reference keeps (super_block.py:185-224, krige3d.py:356-375) -----
+        int tot = 0; // kept entries, compacted to rows 0.. of the lane's column
+        if (active) {
+            if (OCT) {
+                for (int l = 0; l < 8; l++) {
+                    const int n = meta[l * 32 + lane] & 255;
+                    for (int k = 0; k < n; k++) {
+                        const int row = l * cap + k;
+                        const int gf = gidx[row * 32 + lane];
+                        if (gf < 0) continue; // the sample at the location itself
+                        if (tot != row) {
+                            gidx[tot * 32 + lane] = gf;
+                            keys[tot * 32 + lane] = keys[row * 32 + lane];
+                        }
+                        tot++;
+                    }
                 }
-                __syncwarp();
-                warp_bitonic(keys, slots, n, lane);
+            } else {
+                tot = meta[lane] & 255;
             }
-        } else if (staged) {
-            NodeCtx ns = nc;
-            ns.qx = stx; ns.qy = sty; ns.qz = stz;
-            K = prune_list(P, ns, keys, slots, K, lane, ns.excl != 0);
-        } else {
-            K = prune_list_cold(P, nc, keys, slots, K, lane, nc.excl != 0);
         }
-        nhint = K < K3D_NHINT ? K : K3D_NHINT; // this node's neighbours seed the next bounds
-        if (lane < nhint) hint[lane] = slots[lane];
-        const int na = K < P.ndmax ? K : P.ndmax; // krige3d.py:356-375
+        const int na = tot < P.ndmax ? tot : P.ndmax;
+        if ((ordered || tot > P.ndmax) && tot > 1) {
+            // rows 0..na-1 become the na nearest in (distance, index) order
+            for (int j = 0; j < na; j++) {
+                int bi = j;
+                double bk = keys[j * 32 + lane];
+                for (int e = j + 1; e < tot; e++) {
+                    const double k = keys[e * 32 + lane];
+                    bool lt = k < bk;
+                    if (k == bk) lt = gidx[e * 32 + lane] < gidx[bi * 32 + lane];
+                    if (lt) { bk = k; bi = e; }
+                }
+                if (bi != j) {
+                    const int gj = gidx[j * 32 + lane], gb = gidx[bi * 32 + lane];
+                    keys[bi * 32 + lane] = keys[j * 32 + lane];
+                    gidx[bi * 32 + lane] = gj;
+                    keys[j * 32 + lane] = bk;
+                    gidx[j * 32 + lane] = gb;
+                }
+            }
+        }
+        __syncwarp(); // the keys are dead: the output staging overlays them
+        for (int e = 0; e < na; e++) outl[e * 33 + lane] = (unsigned)gidx[e * 32 + lane];
         __syncwarp();
-        for (int i = lane; i < (ordered ? P.ndmax : na); i += 32)
-            nbr[o * P.ndmax + i] = i < na ? (staged ? stidx[slots[i]] : slots[i]) : -1;
-        if (lane == 0) {
+        const int nact = min(32, T.tnodes - base);
+        for (int j = 0; j < nact; j++) { // one coalesced row per node
+            const unsigned long long oj = __shfl_sync(FULL, (unsigned long long)o, j);
+            const int nj = __shfl_sync(FULL, na, j);
+            const int lim = ordered ? P.ndmax : nj;
+            for (int e = lane; e < lim; e += 32)
+                nbr[oj * P.ndmax + e] = e < nj ? (int)outl[e * 33 + j] : -1;
+        }
+        if (active) {
             cnt[o] = na;
             if (ncand_out) ncand_out[o] = tested;
         }
-        __syncwarp();
+        __syncwarp(); // the next pass re-initialises the lists
     }
 }
 
@@ -1154,7 +1062,7 @@ template <int AMAX, bool BLOCK>
 __global__ void __launch_bounds__(AMAX == 5 ? 256 : 640, AMAX == 5 ? K3D_SMALL_CTAS : 1)
 k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
                  const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
-                 const int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
+                 const int tile0, const int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
                  const __grid_constant__ BCfg cfg, const __grid_constant__ PtSet pts)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -1186,7 +1094,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     unsigned short *s_rtab = (unsigned short *)(smem + b_off_rtab(cfg)); // (warp << 8) | round
     __shared__ double s_jloc[20][3]; // per warp: node location
 
-    const Tile T = tile_of_block(P, in, iz0, iz1, pts);
+    const Tile T = tile_of_block(P, in, iz0, iz1, pts, tile0);
     if (T.tnodes <= 0)
         return;
     // structure-space origin of the tile: first node of the super block (slab independent)
@@ -1694,41 +1602,55 @@ void make_prep(const K3dParams *p, KPrep *q)
     q->eps0s = K3D_EPS / (a0 * a0);
 }
 
-// ---- search kernel plan: stage capacity and CTAs per SM --------------------------------
+// ---- search kernel plan: warps per CTA and stage capacity ---------------------------------
 // `mean_cand` is the expected number of candidate samples per tile, `tile_nodes` the mean
-// number of grid nodes per tile.
+// number of grid nodes per tile.  The per-node selection lists (12 B per kept neighbour, in
+// shared memory) set the number of resident warps; the plan takes the CTA width that keeps
+// the most warps on an SM without giving a tile more warps than it has nodes for.
 int make_scfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_max, SCfg *c)
 {
     memset(c, 0, sizeof(*c));
-    c->keepmax = p->noct > 0 ? 8 * p->noct : p->ndmax;
-    c->kcap = 128; // power of two: the bitonic network pads the list up to it
-    while (c->kcap < c->keepmax + 64) c->kcap <<= 1;
-    // a warp's first node has no bounds from a predecessor: keep walks >= ~12 nodes
-    c->warps = tile_nodes >= 96.0 ? 8 : tile_nodes >= 48.0 ? 4 : 2;
+    c->nlist = p->noct > 0 ? 8 : 1;
+    c->cap = p->noct > 0 ? p->noct : p->ndmax;
+    if (c->cap > 255) return K3D_ECAPACITY; // list counters are bytes
+    c->pw_bytes = spw_bytes(*c);
     int want = roundup32((int)(2.0 * mean_cand) + 64);
     if (want < 256) want = 256;
     if (want > 4096) want = 4096;
     int floor_cs = roundup32((int)(1.4 * mean_cand) + 32);
     if (floor_cs < 128) floor_cs = 128;
     if (floor_cs > want) floor_cs = want;
-    for (int pass = 0; pass < 2; pass++) {
-        for (int ctas = 6; ctas >= 1; ctas--) {
+    int wneed = (int)((tile_nodes + 31.0) / 32.0); // warps a tile can keep busy at once
+    if (wneed < 1) wneed = 1;
+    if (wneed > 8) wneed = 8;
+    int force_warps = 0; // tuning knob: K3D_SEARCH_WARPS
+    if (const char *e = getenv("K3D_SEARCH_WARPS")) force_warps = atoi(e);
+    double best = -1.0;
+    SCfg pick = *c;
+    for (int pass = 0; pass < 2 && best < 0.0; pass++) {
+        c->cs = pass == 0 ? want : floor_cs;
+        for (int warps = 1; warps <= 8; warps++) {
+            if (force_warps ? warps != force_warps : warps > wneed) continue;
+            c->warps = warps;
+            const int bytes = s_total_bytes(*c);
             // the driver reserves 1 KB per CTA; 256 B covers the static shared memory
-            const int budget = (smem_max + 1024) / ctas - 1024 - 256;
-            c->cs = 0;
-            const int fixed = s_off_warp(*c) + c->warps * spw_bytes(*c);
-            // per candidate: 24 B coordinates + 4 B index in the stage, 1 B of short list per warp
-            int cs = ((budget - fixed - 64) / (28 + c->warps)) & ~31;
-            if (cs > want) cs = want;
-            if (cs >= (pass == 0 ? want : floor_cs)) {
-                c->cs = cs;
-                c->pw_bytes = spw_bytes(*c);
-                c->smem_bytes = s_off_warp(*c) + c->warps * c->pw_bytes;
-                return K3D_OK;
+            if (bytes + 256 > smem_max) continue;
+            int ctas = (smem_max + 1024) / (bytes + 256 + 1024);
+            if (ctas > 32) ctas = 32;
+            if (ctas * warps > 64) ctas = 64 / warps;
+            // resident warps, discounted by the share of a tile's last pass that idles
+            const double wp = (tile_nodes + 31.0) / 32.0, passes = ceil(wp / warps);
+            const double score = ctas * warps * (wp / (passes * warps)) + 1e-3 * warps;
+            if (score > best) {
+                best = score;
+                pick = *c;
+                pick.smem_bytes = bytes;
             }
         }
     }
-    return K3D_ECAPACITY;
+    if (best < 0.0) return K3D_ECAPACITY;
+    *c = pick;
+    return K3D_OK;
 }
 
 // ---- solve kernel plan: warps per CTA and CTAs per SM -------------------------------------
@@ -1847,7 +1769,7 @@ int raise_smem_limit(const void *func, int dev, int smem_max)
 template <int AMAX, bool BLOCK>
 int launch_solve2(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
                   int iz0, int iz1, const int32_t *nbr, int32_t *cnt, const BCfg &c,
-                  long long ntiles, cudaStream_t st, const PtSet &ps)
+                  int tile0, long long ntiles, cudaStream_t st, const PtSet &ps)
 {
     int dev = 0, smem_max = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -1855,7 +1777,7 @@ int launch_solve2(const K3dParams *p, const KPrep *q, const K3dInputs *in, const
     int rc = raise_smem_limit((const void *)k3d_solve_kernel<AMAX, BLOCK>, dev, smem_max);
     if (rc) return rc;
     k3d_solve_kernel<AMAX, BLOCK><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(
-        *p, *q, *in, *out, iz0, iz1, nbr, cnt, c, ps);
+        *p, *q, *in, *out, iz0, iz1, tile0, nbr, cnt, c, ps);
     CUDA_TRY(cudaGetLastError());
     return K3D_OK;
 }
@@ -1863,10 +1785,26 @@ int launch_solve2(const K3dParams *p, const KPrep *q, const K3dInputs *in, const
 template <int AMAX>
 int launch_solve(const K3dParams *p, const KPrep *q, const K3dInputs *in, const K3dOutputs *out,
                  int iz0, int iz1, const int32_t *nbr, int32_t *cnt, const BCfg &c,
-                 long long ntiles, cudaStream_t st, const PtSet &ps)
+                 int tile0, long long ntiles, cudaStream_t st, const PtSet &ps)
 {
-    return p->ndb > 1 ? launch_solve2<AMAX, true>(p, q, in, out, iz0, iz1, nbr, cnt, c, ntiles, st, ps)
-                      : launch_solve2<AMAX, false>(p, q, in, out, iz0, iz1, nbr, cnt, c, ntiles, st, ps);
+    return p->ndb > 1 ? launch_solve2<AMAX, true>(p, q, in, out, iz0, iz1, nbr, cnt, c, tile0, ntiles, st, ps)
+                      : launch_solve2<AMAX, false>(p, q, in, out, iz0, iz1, nbr, cnt, c, tile0, ntiles, st, ps);
+}
+
+template <bool PTS, bool OCT>
+int launch_search(const K3dParams *p, const K3dInputs *in, int iz0, int iz1, int tile0,
+                  long long ntiles, int32_t *nbr, int32_t *cnt, int32_t *ncand, int ordered,
+                  const SCfg &c, cudaStream_t st, const PtSet &ps)
+{
+    int dev = 0, smem_max = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int rc = raise_smem_limit((const void *)k3d_search_kernel<PTS, OCT>, dev, smem_max);
+    if (rc) return rc;
+    k3d_search_kernel<PTS, OCT><<<(unsigned)ntiles, c.warps * 32, c.smem_bytes, st>>>(
+        *p, *in, iz0, iz1, tile0, nbr, cnt, ncand, ordered, c, ps);
+    CUDA_TRY(cudaGetLastError());
+    return K3D_OK;
 }
 
 } // namespace
@@ -1955,9 +1893,6 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
     if (ntiles > 0x7fffffffLL) return fail(K3D_EINVAL, "too many tiles");
     KPrep q;
     make_prep(p, &q);
-    if ((rc = raise_smem_limit((const void *)k3d_search_kernel<false>, dev, smem_max)) != K3D_OK ||
-        (rc = raise_smem_limit((const void *)k3d_search_kernel<true>, dev, smem_max)) != K3D_OK)
-        return rc;
 
     // neighbour lists travel from the search kernel to the solve kernel through global
     // memory: the caller's arrays when given, else stream-ordered scratch, at most ~4 GB at
@@ -2014,20 +1949,33 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
         if (co.ncand) co.ncand += shift;
         int32_t *nbr = co.nbr_idx ? co.nbr_idx : snbr;
         int32_t *cnt = co.nbr_cnt ? co.nbr_cnt : scnt;
+        // only the super-block layers that can meet planes [za, zb) are launched (one layer
+        // of slack on each side: the exact layer of a plane is in the device-side table)
+        int tile0 = 0;
+        long long ntl = ntiles;
+        if (!pts) {
+            int l0 = (int)((double)za * p->nzsup / p->nz) - 1;
+            int l1 = (int)((double)(zb - 1) * p->nzsup / p->nz) + 1;
+            l0 = l0 < 0 ? 0 : l0;
+            l1 = l1 >= p->nzsup ? p->nzsup - 1 : l1;
+            tile0 = l0 * p->nxsup * p->nysup;
+            ntl = (long long)(l1 - l0 + 1) * p->nxsup * p->nysup;
+        }
+        const int sz0 = pts ? 0 : za, sz1 = pts ? p->nz : zb, ordered = co.nbr_idx ? 1 : 0;
         cudaEventRecord(g_ev[0], st);
         if (pts)
-            k3d_search_kernel<true><<<(unsigned)ntiles, sc.warps * 32, sc.smem_bytes, st>>>(
-                *p, ci, 0, p->nz, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc, ps);
+            rc = p->noct > 0 ? launch_search<true, true>(p, &ci, sz0, sz1, tile0, ntl, nbr, cnt, co.ncand, ordered, sc, st, ps)
+                             : launch_search<true, false>(p, &ci, sz0, sz1, tile0, ntl, nbr, cnt, co.ncand, ordered, sc, st, ps);
         else
-            k3d_search_kernel<false><<<(unsigned)ntiles, sc.warps * 32, sc.smem_bytes, st>>>(
-                *p, ci, za, zb, nbr, cnt, co.ncand, co.nbr_idx ? 1 : 0, sc, ps);
-        if (cudaGetLastError() != cudaSuccess) { rc = fail(K3D_ECUDA, "search kernel launch failed"); break; }
+            rc = p->noct > 0 ? launch_search<false, true>(p, &ci, sz0, sz1, tile0, ntl, nbr, cnt, co.ncand, ordered, sc, st, ps)
+                             : launch_search<false, false>(p, &ci, sz0, sz1, tile0, ntl, nbr, cnt, co.ncand, ordered, sc, st, ps);
+        if (rc) break;
         cudaEventRecord(g_ev[1], st);
         switch (amax_for(bc.rtot)) {
-        case 5: rc = launch_solve<5>(p, &q, &ci, &co, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, bc, ntiles, st, ps); break;
-        case 9: rc = launch_solve<9>(p, &q, &ci, &co, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, bc, ntiles, st, ps); break;
-        case 11: rc = launch_solve<11>(p, &q, &ci, &co, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, bc, ntiles, st, ps); break;
-        default: rc = launch_solve<0>(p, &q, &ci, &co, pts ? 0 : za, pts ? p->nz : zb, nbr, cnt, bc, ntiles, st, ps); break;
+        case 5: rc = launch_solve<5>(p, &q, &ci, &co, sz0, sz1, nbr, cnt, bc, tile0, ntl, st, ps); break;
+        case 9: rc = launch_solve<9>(p, &q, &ci, &co, sz0, sz1, nbr, cnt, bc, tile0, ntl, st, ps); break;
+        case 11: rc = launch_solve<11>(p, &q, &ci, &co, sz0, sz1, nbr, cnt, bc, tile0, ntl, st, ps); break;
+        default: rc = launch_solve<0>(p, &q, &ci, &co, sz0, sz1, nbr, cnt, bc, tile0, ntl, st, ps); break;
         }
         cudaEventRecord(g_ev[2], st);
         g_ev_pending = true;
@@ -2041,7 +1989,7 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
     g_launch.smem_bytes = bc.smem_bytes;
     g_launch.warps_per_cta = bc.warps;
     g_launch.stage_capacity = sc.cs;
-    g_launch.list_capacity = sc.kcap;
+    g_launch.list_capacity = sc.nlist * sc.cap;
     g_launch.search_block = sc.warps * 32;
     g_launch.search_smem_bytes = sc.smem_bytes;
     return K3D_OK;
