@@ -97,7 +97,8 @@ void drop_events()
 // the lists into estimates.  Both work tile by tile (tile = grid nodes of one super block).
 struct SCfg {       // search kernel
     int warps;      // warps per CTA
-    int cs;         // staged candidate capacity per CTA
+    int cs;         // candidates a tile may list before the cull (temporaries, overlaid)
+    int cst;        // staged candidates per CTA: those within reach of the tile, sorted
     int cap;        // entries per selection list: noct (octant search) or ndmax
     int nlist;      // selection lists per node: 8 octants, or 1
     int pw_bytes;   // per-warp shared bytes
@@ -137,16 +138,14 @@ __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 // shared memory carve-up (bytes from the dynamic smem base)
 // search kernel
-//   CTA : [stage x,y,z f64 x cs][stage sample index i32 x cs][stage bin u8 x cs]
+//   CTA : [stage: records of (x, y, z f64, sample index i32, bin i32) x cst+4]
 //         [run table i32 x 3*threads][bin histogram u16 x warps*SBINS][bin start u16 x SBINS+1]
 //         [reduction scratch f64 x 8*6]
 //   warp: [keys f64 x E*32][gidx i32 x E*32][tau f64 x nlist*32][meta u16 x nlist*32]
 //         E = nlist*cap entries per node, lane-interleaved: entry e of lane l at e*32 + l
 //   The staging temporaries (the candidates before the sort: sample index i32, rank u16,
 //   bin u8 each) overlay the per-warp regions, which are initialised afterwards.
-__host__ __device__ inline int s_off_sg(const SCfg &c) { return c.cs * 24; }
-__host__ __device__ inline int s_off_sbin(const SCfg &c) { return c.cs * 28; }
-__host__ __device__ inline int s_off_chunk(const SCfg &c) { return align16(c.cs * 29); }
+__host__ __device__ inline int s_off_chunk(const SCfg &c) { return (c.cst + 4) * 32; }
 __host__ __device__ inline int s_off_whist(const SCfg &c) { return s_off_chunk(c) + c.warps * 32 * 12; }
 __host__ __device__ inline int s_off_bstart(const SCfg &c) { return s_off_whist(c) + c.warps * K3D_SBINS * 2; }
 __host__ __device__ inline int s_off_red(const SCfg &c) { return align16(s_off_bstart(c) + (K3D_SBINS + 1) * 2); }
@@ -657,7 +656,7 @@ __device__ __forceinline__ void snake_node(const Tile &T, int t, int &lx, int &l
 // instantiation, so that the grid kernel carries none of the coincident-sample logic.
 // OCT: octant search (noct > 0).
 template <bool PTS, bool OCT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const int iz0,
                   const int iz1, const int tile0, int32_t *__restrict__ nbr,
                   int32_t *__restrict__ cnt, int32_t *__restrict__ ncand_out, const int ordered,
@@ -667,11 +666,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NT = cfg.warps * 32;
 
-    double *stx = (double *)smem;
-    double *sty = stx + cfg.cs;
-    double *stz = sty + cfg.cs;
-    int *stg = (int *)(smem + s_off_sg(cfg));
-    unsigned char *sbin = smem + s_off_sbin(cfg);
+    double *st4 = (double *)smem; // staged candidates: x, y, z, (sample index | bin << 32)
     int *chunk = (int *)(smem + s_off_chunk(cfg)); // [3][NT]: lo, cnt, off of a batch of runs
     unsigned short *whist = (unsigned short *)(smem + s_off_whist(cfg));
     unsigned short *bstart = (unsigned short *)(smem + s_off_bstart(cfg));
@@ -741,7 +736,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         }
         __syncthreads();
     }
-    const bool staged = total <= cfg.cs; // else: every thread walks the runs in global memory
+    bool staged = total <= cfg.cs; // else: every thread walks the runs in global memory
 
     // ---- 2. centre of the tile's nodes and their largest distance from it ------------------
     double cx, cy, cz, ex, ey, ez;
@@ -845,20 +840,24 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
             if (lane == 31) bstart[K3D_SBINS] = (unsigned short)incl;
         }
         __syncthreads();
-        for (int i0 = wbeg; i0 < wend; i0 += 32) {
+        staged = (int)bstart[K3D_SBINS] <= cfg.cst; // what is within reach must fit the stage
+        for (int i0 = wbeg; staged && i0 < wend; i0 += 32) {
             const int i = i0 + lane;
             if (i < wend) {
                 const int bin = btmp[i];
                 if (bin != 255) {
                     const int pos = bstart[bin] + whist[warp * K3D_SBINS + bin] + rtmp[i];
                     const int g = gtmp[i];
-                    stx[pos] = in.sx[g];
-                    sty[pos] = in.sy[g];
-                    stz[pos] = in.sz[g];
-                    stg[pos] = g;
-                    sbin[pos] = (unsigned char)bin;
+                    double2 *rec = reinterpret_cast<double2 *>(st4 + 4 * pos);
+                    rec[0] = make_double2(in.sx[g], in.sy[g]);
+                    rec[1] = make_double2(in.sz[g], __hiloint2double(bin, g));
                 }
             }
+        }
+        if (staged && tid < 4) { // the stream is read four records at a time: pad with far-away samples
+            double2 *rec = reinterpret_cast<double2 *>(st4 + 4 * ((int)bstart[K3D_SBINS] + tid));
+            rec[0] = make_double2(1e150, 1e150);
+            rec[1] = make_double2(1e150, __hiloint2double(255, 0));
         }
         __syncthreads();
     }
@@ -870,7 +869,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     int *gidx = (int *)((unsigned char *)keys + E * 256);  // [E][32] sample index (bit 31: the
                                                            //  sample at the location itself)
     double *tau = (double *)((unsigned char *)keys + E * 384);          // [nlist][32] farthest kept
-    unsigned short *meta = (unsigned short *)((unsigned char *)tau + nlist * 256); // count | argmax << 8
+    unsigned short *count = (unsigned short *)((unsigned char *)tau + nlist * 256);  // [nlist][32]
     unsigned *outl = (unsigned *)keys; // [ndmax][33] output staging, once the keys are dead
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const unsigned GM = 0x7fffffffu;
@@ -899,7 +898,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         }
         for (int l = 0; l < nlist; l++) {
             tau[l * 32 + lane] = INF; // a list that is not full accepts anything in the radius
-            meta[l * 32 + lane] = 0;
+            count[l * 32 + lane] = 0;
         }
         const double rho = sqrt(sqdist_exact(xloc - cx, yloc - cy, zloc - cz, rs));
         // candidates whose squared distance from the centre exceeds `limit` cannot be kept
@@ -911,49 +910,56 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         bool done = !active, changed = false;
         int tested = 0;
 
-        auto consider = [&](double sx_, double sy_, double sz_, int g) {
-            // point1 = node, point2 = sample (super_block.py:301-305)
-            const double dx = __dsub_rn(xloc, sx_), dy = __dsub_rn(yloc, sy_), dz = __dsub_rn(zloc, sz_);
-            const double h = sqdist_exact(dx, dy, dz, rs);
-            if (h > P.radsqd) return; // super_block.py:306
-            int l = 0;
-            unsigned gf = (unsigned)g;
-            if (OCT) l = octant_of_neg(dx, dy, dz);
-            if (PTS && excl && coincident(dx, dy, dz)) { // krige3d.py:359-363
-                if (!OCT) return;      // never a candidate
-                gf |= ~GM;             // takes its place in the octant, dropped afterwards
-            }
+        // the list of a candidate at squared distance h (octant l), sample index gf
+        // Puts a candidate (octant l, squared distance h, sample index gf) into its list, kept
+        // sorted by (distance, index): entries farther than the newcomer move up one place,
+        // the farthest falls off a full list.  The stream arrives roughly nearest first, so
+        // the newcomer usually lands at or next to the end.
+        auto keep = [&](int l, double h, unsigned gf) {
             const double tl = tau[l * 32 + lane];
             if (h > tl) return;
-            const int m = meta[l * 32 + lane];
-            int n = m & 255;
-            const int im = m >> 8, row0 = l * cap;
+            int n = count[l * 32 + lane], e;
+            const int row0 = l * cap;
             if (n == cap) { // full: it must beat the farthest kept, (tl, index) lexicographically
-                if (h == tl && (gf & GM) > ((unsigned)gidx[(row0 + im) * 32 + lane] & GM)) return;
-                keys[(row0 + im) * 32 + lane] = h;
-                gidx[(row0 + im) * 32 + lane] = (int)gf;
+                e = cap - 1;
+                if (h == tl && (gf & GM) > ((unsigned)gidx[(row0 + e) * 32 + lane] & GM)) return;
             } else {
-                keys[(row0 + n) * 32 + lane] = h;
-                gidx[(row0 + n) * 32 + lane] = (int)gf;
-                n++;
-                if (n < cap) {
-                    meta[l * 32 + lane] = (unsigned short)(n | (im << 8));
-                    return;
-                }
+                e = n++;
+                count[l * 32 + lane] = (unsigned short)n;
             }
-            // the list is full: its farthest entry, largest (distance, index), is the new bound
-            int bi = 0;
-            double bk = keys[row0 * 32 + lane];
-            for (int e = 1; e < cap; e++) {
-                const double k = keys[(row0 + e) * 32 + lane];
-                bool gt = k > bk;
-                if (k == bk)
-                    gt = ((unsigned)gidx[(row0 + e) * 32 + lane] & GM) > ((unsigned)gidx[(row0 + bi) * 32 + lane] & GM);
-                if (gt) { bk = k; bi = e; }
+            double last = h; // what ends up in the last place
+            bool first = true;
+            while (e > 0) {
+                const double k = keys[(row0 + e - 1) * 32 + lane];
+                if (k < h) break;
+                const unsigned gk = (unsigned)gidx[(row0 + e - 1) * 32 + lane];
+                if (k == h && (gk & GM) < (gf & GM)) break;
+                keys[(row0 + e) * 32 + lane] = k;
+                gidx[(row0 + e) * 32 + lane] = (int)gk;
+                if (first) { last = k; first = false; }
+                e--;
             }
-            tau[l * 32 + lane] = bk;
-            meta[l * 32 + lane] = (unsigned short)(cap | (bi << 8));
-            changed = true;
+            keys[(row0 + e) * 32 + lane] = h;
+            gidx[(row0 + e) * 32 + lane] = (int)gf;
+            if (n == cap) { // a full list bounds what can still be kept
+                tau[l * 32 + lane] = last;
+                changed = true;
+            }
+        };
+        // squared search distance of a sample from the node, its octant and whether it may be
+        // used at all; point1 = node, point2 = sample (super_block.py:301-305)
+        auto measure = [&](double sx_, double sy_, double sz_, int g, double &h, int &l, unsigned &gf) {
+            const double dx = __dsub_rn(xloc, sx_), dy = __dsub_rn(yloc, sy_), dz = __dsub_rn(zloc, sz_);
+            h = sqdist_exact(dx, dy, dz, rs);
+            l = OCT ? octant_of_neg(dx, dy, dz) : 0;
+            gf = (unsigned)g;
+            // super_block.py:306, and the list's bound as it stands (keep() looks again)
+            bool ok = !(h > P.radsqd) && !(h > tau[l * 32 + lane]);
+            if (PTS && excl && coincident(dx, dy, dz)) { // krige3d.py:359-363
+                if (OCT) gf |= ~GM;    // takes its place in the octant, dropped afterwards
+                else ok = false;       // never a candidate
+            }
+            return ok;
         };
 
         if (staged) {
@@ -965,12 +971,28 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                         limit = limit_of(tmax);
                         changed = false;
                     }
-                    done = (double)sbin[c0] * binw > limit;
+                    done = (double)__double2hiint(st4[4 * c0 + 3]) * binw > limit;
                 }
                 if (__all_sync(FULL, done)) break;
                 if (!done) {
+                    // four candidates at a time: their distances are independent work, which
+                    // hides the latency of the dependent fp64 chain of each
                     const int c1 = min(c0 + K3D_SCHUNK, nsorted);
-                    for (int c = c0; c < c1; c++) consider(stx[c], sty[c], stz[c], stg[c]);
+                    for (int c = c0; c < c1; c += 4) {
+                        double h[4];
+                        int l[4];
+                        unsigned gf[4];
+                        bool ok[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const double2 *rec = reinterpret_cast<const double2 *>(st4 + 4 * (c + j));
+                            const double2 a = rec[0], b = rec[1];
+                            ok[j] = measure(a.x, a.y, b.x, __double2loint(b.y), h[j], l[j], gf[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (ok[j]) keep(l[j], h[j], gf[j]);
+                    }
                     tested += c1 - c0;
                 }
             }
@@ -986,7 +1008,12 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                 const int b = (bz * P.nysup + by) * P.nxsup;
                 const int lo = in.sbstart[b + bx0], hi = in.sbstart[b + bx1 + 1];
                 if (active)
-                    for (int i = lo; i < hi; i++) consider(in.sx[i], in.sy[i], in.sz[i], i);
+                    for (int i = lo; i < hi; i++) {
+                        double h;
+                        int l;
+                        unsigned gf;
+                        if (measure(in.sx[i], in.sy[i], in.sz[i], i, h, l, gf)) keep(l, h, gf);
+                    }
                 tested += hi - lo;
             }
         }
@@ -996,7 +1023,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         if (active) {
             if (OCT) {
                 for (int l = 0; l < 8; l++) {
-                    const int n = meta[l * 32 + lane] & 255;
+                    const int n = count[l * 32 + lane];
                     for (int k = 0; k < n; k++) {
                         const int row = l * cap + k;
                         const int gf = gidx[row * 32 + lane];
@@ -1009,11 +1036,11 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                     }
                 }
             } else {
-                tot = meta[lane] & 255;
+                tot = count[lane];
             }
         }
         const int na = tot < P.ndmax ? tot : P.ndmax;
-        if ((ordered || tot > P.ndmax) && tot > 1) {
+        if (OCT && (ordered || tot > P.ndmax) && tot > 1) { // (a single list is sorted already)
             // rows 0..na-1 become the na nearest in (distance, index) order
             for (int j = 0; j < na; j++) {
                 int bi = j;
@@ -1037,12 +1064,31 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         for (int e = 0; e < na; e++) outl[e * 33 + lane] = (unsigned)gidx[e * 32 + lane];
         __syncwarp();
         const int nact = min(32, T.tnodes - base);
-        for (int j = 0; j < nact; j++) { // one coalesced row per node
-            const unsigned long long oj = __shfl_sync(FULL, (unsigned long long)o, j);
-            const int nj = __shfl_sync(FULL, na, j);
-            const int lim = ordered ? P.ndmax : nj;
-            for (int e = lane; e < lim; e += 32)
-                nbr[oj * P.ndmax + e] = e < nj ? (int)outl[e * 33 + j] : -1;
+        const int pieces = P.ndmax >> 2; // 16-byte pieces of a node's row
+        if ((P.ndmax & 3) == 0 && (pieces & (pieces - 1)) == 0 && pieces <= 16) {
+            // 32 / pieces nodes per step, one int4 per lane: coalesced 128-bit stores
+            const int nps = 32 / pieces, jn = lane / pieces, e0 = 4 * (lane % pieces);
+            for (int j0 = 0; j0 < nact; j0 += nps) {
+                const int j = j0 + jn, src = j < 32 ? j : 31;
+                const unsigned long long oj = __shfl_sync(FULL, (unsigned long long)o, src);
+                const int nj = __shfl_sync(FULL, na, src);
+                if (j < nact && e0 < (ordered ? P.ndmax : nj)) {
+                    int4 v;
+                    v.x = e0 < nj ? (int)outl[e0 * 33 + j] : -1;
+                    v.y = e0 + 1 < nj ? (int)outl[(e0 + 1) * 33 + j] : -1;
+                    v.z = e0 + 2 < nj ? (int)outl[(e0 + 2) * 33 + j] : -1;
+                    v.w = e0 + 3 < nj ? (int)outl[(e0 + 3) * 33 + j] : -1;
+                    *reinterpret_cast<int4 *>(nbr + oj * P.ndmax + e0) = v;
+                }
+            }
+        } else {
+            for (int j = 0; j < nact; j++) { // one coalesced row per node
+                const unsigned long long oj = __shfl_sync(FULL, (unsigned long long)o, j);
+                const int nj = __shfl_sync(FULL, na, j);
+                const int lim = ordered ? P.ndmax : nj;
+                for (int e = lane; e < lim; e += 32)
+                    nbr[oj * P.ndmax + e] = e < nj ? (int)outl[e * 33 + j] : -1;
+            }
         }
         if (active) {
             cnt[o] = na;
@@ -1614,13 +1660,15 @@ int make_scfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_
     c->cap = p->noct > 0 ? p->noct : p->ndmax;
     if (c->cap > 255) return K3D_ECAPACITY; // list counters are bytes
     c->pw_bytes = spw_bytes(*c);
-    int want = roundup32((int)(2.0 * mean_cand) + 64);
-    if (want < 256) want = 256;
+    // the stage holds what is within reach of the tile (typically 60 % of what the template
+    // lists); a tile that needs more walks global memory instead (tested)
+    int want = roundup32((int)(1.25 * mean_cand) + 64);
+    if (want < 128) want = 128;
     if (want > 4096) want = 4096;
-    int floor_cs = roundup32((int)(1.4 * mean_cand) + 32);
-    if (floor_cs < 128) floor_cs = 128;
-    if (floor_cs > want) floor_cs = want;
-    int wneed = (int)((tile_nodes + 31.0) / 32.0); // warps a tile can keep busy at once
+    int floor_cst = roundup32((int)(0.9 * mean_cand) + 32);
+    if (floor_cst < 96) floor_cst = 96;
+    if (floor_cst > want) floor_cst = want;
+    int wneed = (int)ceil(tile_nodes / 32.0); // warps a tile can keep busy at once
     if (wneed < 1) wneed = 1;
     if (wneed > 8) wneed = 8;
     int force_warps = 0; // tuning knob: K3D_SEARCH_WARPS
@@ -1628,19 +1676,23 @@ int make_scfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_
     double best = -1.0;
     SCfg pick = *c;
     for (int pass = 0; pass < 2 && best < 0.0; pass++) {
-        c->cs = pass == 0 ? want : floor_cs;
+        c->cst = pass == 0 ? want : floor_cst;
         for (int warps = 1; warps <= 8; warps++) {
             if (force_warps ? warps != force_warps : warps > wneed) continue;
             c->warps = warps;
+            // the unsorted candidate list overlays the selection lists: 7 bytes each
+            c->cs = roundup32((int)(2.5 * mean_cand) + 64);
+            if (c->cs < warps * c->pw_bytes / 7) c->cs = (warps * c->pw_bytes / 7) & ~31;
+            if (c->cs > 8192) c->cs = 8192;
             const int bytes = s_total_bytes(*c);
             // the driver reserves 1 KB per CTA; 256 B covers the static shared memory
             if (bytes + 256 > smem_max) continue;
             int ctas = (smem_max + 1024) / (bytes + 256 + 1024);
             if (ctas > 32) ctas = 32;
-            if (ctas * warps > 64) ctas = 64 / warps;
-            // resident warps, discounted by the share of a tile's last pass that idles
-            const double wp = (tile_nodes + 31.0) / 32.0, passes = ceil(wp / warps);
-            const double score = ctas * warps * (wp / (passes * warps)) + 1e-3 * warps;
+            if (ctas * warps > 16) ctas = 16 / warps > 0 ? 16 / warps : 1; // ~120 registers per thread
+            // resident warps, discounted by the share of a tile's warp slots that idle
+            const double wp = ceil(tile_nodes / 32.0), passes = ceil(wp / warps);
+            const double score = ctas * warps * ((tile_nodes / 32.0) / (passes * warps)) + 1e-3 * warps;
             if (score > best) {
                 best = score;
                 pick = *c;
@@ -1988,7 +2040,7 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
     g_launch.block = bc.warps * 32;
     g_launch.smem_bytes = bc.smem_bytes;
     g_launch.warps_per_cta = bc.warps;
-    g_launch.stage_capacity = sc.cs;
+    g_launch.stage_capacity = sc.cst;
     g_launch.list_capacity = sc.nlist * sc.cap;
     g_launch.search_block = sc.warps * 32;
     g_launch.search_smem_bytes = sc.smem_bytes;
