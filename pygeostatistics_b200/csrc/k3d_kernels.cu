@@ -152,8 +152,8 @@ __host__ __device__ inline int s_off_red(const SCfg &c) { return align16(s_off_b
 __host__ __device__ inline int s_off_warp(const SCfg &c) { return align16(s_off_red(c) + 8 * 6 * 8); }
 __host__ __device__ inline int spw_bytes(const SCfg &c)
 {
-    const int E = c.nlist * c.cap;
-    return align16(E * 384 + c.nlist * 256 + c.nlist * 64);
+    const int E = c.nlist * c.cap; // (8 bounds per lane: octants, or the groups of the one list)
+    return align16(E * 384 + 8 * 256 + 8 * 64);
 }
 __host__ __device__ inline int s_total_bytes(const SCfg &c)
 {
@@ -869,7 +869,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     int *gidx = (int *)((unsigned char *)keys + E * 256);  // [E][32] sample index (bit 31: the
                                                            //  sample at the location itself)
     double *tau = (double *)((unsigned char *)keys + E * 384);          // [nlist][32] farthest kept
-    unsigned short *count = (unsigned short *)((unsigned char *)tau + nlist * 256);  // [nlist][32]
+    unsigned short *count = (unsigned short *)((unsigned char *)tau + 8 * 256);       // [8][32]
     unsigned *outl = (unsigned *)keys; // [ndmax][33] output staging, once the keys are dead
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const unsigned GM = 0x7fffffffu;
@@ -911,11 +911,62 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         int tested = 0;
 
         // the list of a candidate at squared distance h (octant l), sample index gf
-        // Puts a candidate (octant l, squared distance h, sample index gf) into its list, kept
-        // sorted by (distance, index): entries farther than the newcomer move up one place,
-        // the farthest falls off a full list.  The stream arrives roughly nearest first, so
-        // the newcomer usually lands at or next to the end.
+        // Octant search: puts a candidate (octant l, squared distance h, sample index gf) into
+        // its list, kept sorted by (distance, index): entries farther than the newcomer move up
+        // one place, the farthest falls off a full list.  The stream arrives roughly nearest
+        // first, so the newcomer usually lands at or next to the end.
+        // Without octants the one list of ndmax entries is kept UNSORTED in `ng` interleaved
+        // groups (rows g, g + ng, ...) whose farthest entries are tracked (tau[g], count[g] =
+        // its row); the farthest of all (gtau, vrow: registers) is what a newcomer replaces,
+        // after which one group and the ng group maxima are looked at again: 4 + 8 loads
+        // instead of 32.
+        double gtau = INF; // (no octants) bound of the list: farthest kept once it is full
+        int gn = 0, vrow = 0;
+        const int ng = cap >= 16 ? 8 : cap >= 8 ? 4 : 1;
+        auto farthest_of_group = [&](int g) {
+            int bi = g;
+            double bk = keys[g * 32 + lane];
+            for (int r = g + ng; r < cap; r += ng) {
+                const double k = keys[r * 32 + lane];
+                bool gt = k > bk;
+                if (k == bk) gt = ((unsigned)gidx[r * 32 + lane] & GM) > ((unsigned)gidx[bi * 32 + lane] & GM);
+                if (gt) { bk = k; bi = r; }
+            }
+            tau[g * 32 + lane] = bk;
+            count[g * 32 + lane] = (unsigned short)bi;
+        };
+        auto farthest_of_all = [&]() {
+            int bg = 0;
+            double bk = tau[lane];
+            for (int g = 1; g < ng; g++) {
+                const double k = tau[g * 32 + lane];
+                bool gt = k > bk;
+                if (k == bk)
+                    gt = ((unsigned)gidx[count[g * 32 + lane] * 32 + lane] & GM) >
+                         ((unsigned)gidx[count[bg * 32 + lane] * 32 + lane] & GM);
+                if (gt) { bk = k; bg = g; }
+            }
+            gtau = bk;
+            vrow = count[bg * 32 + lane];
+            changed = true;
+        };
         auto keep = [&](int l, double h, unsigned gf) {
+            if constexpr (!OCT) {
+                if (h > gtau) return;
+                if (gn < cap) {
+                    keys[gn * 32 + lane] = h;
+                    gidx[gn * 32 + lane] = (int)gf;
+                    if (++gn < cap) return;
+                    for (int g = 0; g < ng; g++) farthest_of_group(g); // full: the bounds start
+                } else { // it must beat the farthest kept, (gtau, index) lexicographically
+                    if (h == gtau && (gf & GM) > ((unsigned)gidx[vrow * 32 + lane] & GM)) return;
+                    keys[vrow * 32 + lane] = h;
+                    gidx[vrow * 32 + lane] = (int)gf;
+                    farthest_of_group(vrow % ng);
+                }
+                farthest_of_all();
+                return;
+            }
             const double tl = tau[l * 32 + lane];
             if (h > tl) return;
             int n = count[l * 32 + lane], e;
@@ -954,7 +1005,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
             l = OCT ? octant_of_neg(dx, dy, dz) : 0;
             gf = (unsigned)g;
             // super_block.py:306, and the list's bound as it stands (keep() looks again)
-            bool ok = !(h > P.radsqd) && !(h > tau[l * 32 + lane]);
+            bool ok = !(h > P.radsqd) && !(h > (OCT ? tau[l * 32 + lane] : gtau));
             if (PTS && excl && coincident(dx, dy, dz)) { // krige3d.py:359-363
                 if (OCT) gf |= ~GM;    // takes its place in the octant, dropped afterwards
                 else ok = false;       // never a candidate
@@ -966,7 +1017,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
             for (int c0 = 0; c0 < nsorted; c0 += K3D_SCHUNK) {
                 if (!done) {
                     if (changed) { // a bound moved: what is the farthest anything can still be?
-                        double tmax = tau[lane];
+                        double tmax = OCT ? tau[lane] : gtau;
                         for (int l = 1; l < nlist; l++) tmax = fmax(tmax, tau[l * 32 + lane]);
                         limit = limit_of(tmax);
                         changed = false;
@@ -1036,11 +1087,11 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                     }
                 }
             } else {
-                tot = count[lane];
+                tot = gn;
             }
         }
         const int na = tot < P.ndmax ? tot : P.ndmax;
-        if (OCT && (ordered || tot > P.ndmax) && tot > 1) { // (a single list is sorted already)
+        if ((ordered || tot > P.ndmax) && tot > 1) {
             // rows 0..na-1 become the na nearest in (distance, index) order
             for (int j = 0; j < na; j++) {
                 int bi = j;
