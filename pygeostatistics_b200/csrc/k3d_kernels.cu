@@ -922,7 +922,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         // instead of 32.
         double gtau = INF; // (no octants) bound of the list: farthest kept once it is full
         int gn = 0, vrow = 0;
-        const int ng = cap >= 16 ? 8 : cap >= 8 ? 4 : 1;
+        const int ng = cap >= 32 ? 8 : cap >= 12 ? 4 : cap >= 6 ? 2 : 1;
         auto farthest_of_group = [&](int g) {
             int bi = g;
             double bk = keys[g * 32 + lane];
@@ -1155,8 +1155,11 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
 // ---------------------------------------------------------------------------
 // BLOCK: block kriging (ndb > 1), whose right-hand side averages over the block points
 // (one round per part of the discretisation, partial sums added up by the owner warp).
+// registers per thread: 96 (20 warps per SM) up to 36 rows; the 44-row solver keeps 35 doubles
+// of the matrix per lane and spills at 96 (c4: 126 ms against 99.5 ms), so it runs 16 warps of 128
+#define K3D_BIG_THREADS(AMAX) ((AMAX) == 11 ? 512 : 640)
 template <int AMAX, bool BLOCK>
-__global__ void __launch_bounds__(AMAX == 5 ? 256 : 640, AMAX == 5 ? K3D_SMALL_CTAS : 1)
+__global__ void __launch_bounds__(AMAX == 5 ? 256 : K3D_BIG_THREADS(AMAX), AMAX == 5 ? K3D_SMALL_CTAS : 1)
 k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KPrep Q,
                  const K3dInputs in, const K3dOutputs out, const int iz0, const int iz1,
                  const int tile0, const int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
@@ -1781,11 +1784,12 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
     // per / (per + 4) with per = nodes per warp and tile.  Registers cap an SM at 20 warps
     // (102 per thread; 24 warps of 85 for the small-system kernel, whose CTAs hold <= 8 warps).
     const bool small = amax == 5;
-    const int max_cta_warps = small ? 8 : 20, max_sm_warps = small ? 24 : 20;
+    const int big_warps = amax == 11 ? 16 : 20; // K3D_BIG_THREADS
+    const int max_cta_warps = small ? 8 : big_warps, max_sm_warps = small ? 24 : big_warps;
     static const int shapes[][2] = {{2, 10}, {1, 20}, {1, 18}, {2, 8}, {1, 16}, {1, 14}, {2, 6},
                                     {1, 12}, {1, 10}, {2, 4}, {1, 8}, {1, 6}, {1, 4},
                                     {3, 8}, {3, 6}, {3, 5}, {4, 4}, {5, 3}, {8, 2}, {6, 2}, {4, 2},
-                                    {3, 4}, {12, 2}, {6, 4}};
+                                    {3, 4}, {12, 2}, {6, 4}, {4, 5}, {5, 4}, {10, 2}, {6, 3}, {7, 2}, {2, 9}, {2, 7}, {3, 7}};
     double best = -1.0;
     BCfg pick = *c;
     int force_ctas = 0, force_warps = 0; // tuning knob: K3D_SOLVE_SHAPE="ctas,warps"
@@ -1808,8 +1812,10 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
         c->warps = warps;
         const int bytes = b_off_warp(*c) + warps * bpw_bytes(*c);
         if (bytes > budget) continue;
+        // (measured on c3/c4: CTAs of 2-4 warps lose 5-10 % to the imbalance of a small
+        // covariance pool, whatever their number per SM)
         const double per = tile_nodes / warps;
-        const double score = ctas * warps * per / (per + 4.0);
+        const double score = ctas * warps * per / (per + 4.0) * warps / (warps + 2.0);
         if (score > best) {
             best = score;
             c->pw_bytes = bpw_bytes(*c);
