@@ -17,9 +17,11 @@ octant search (`noct`), block kriging (`nxdis/nydis/nzdis`), `itrend`, and the g
 output file (`outfl`, via write_output()).
 """
 import ctypes as C
+import mmap
+import os
 import time
 import weakref
-from collections import namedtuple
+from collections import OrderedDict, namedtuple
 
 import numpy as np
 import torch
@@ -75,6 +77,10 @@ def gather_slabs(local, ranges, plane, group=None):
     import torch.distributed as dist
     world = len(ranges)
     maxp = max(b - a for a, b in ranges)
+    if all(b - a == maxp for a, b in ranges):  # equal slabs: straight into the result
+        full = torch.empty(world * maxp * plane, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, local.contiguous(), group=group)
+        return full
     pad = torch.zeros(maxp * plane, dtype=local.dtype, device=local.device)
     pad[:local.numel()] = local
     full = torch.empty(world * maxp * plane, dtype=local.dtype, device=local.device)
@@ -82,6 +88,101 @@ def gather_slabs(local, ranges, plane, group=None):
     parts = [full[r * maxp * plane: r * maxp * plane + (b - a) * plane]
              for r, (a, b) in enumerate(ranges)]
     return torch.cat(parts)
+
+
+def data_fingerprint(vr):
+    """Cheap checksum of a record array's bytes (sum, xor and a position-weighted sum of its
+    64-bit words): changes with any edit of a value and with any re-ordering of the rows."""
+    raw = np.ascontiguousarray(vr).view(np.uint8).reshape(-1)
+    words = raw[:raw.size // 8 * 8].view(np.uint64)
+    weights = np.arange(1, words.size + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over='ignore'):
+        return (vr.dtype.descr.__repr__(), int(words.size), int(words.sum(dtype=np.uint64)),
+                int(np.bitwise_xor.reduce(words)) if words.size else 0,
+                int((words * weights).sum(dtype=np.uint64)), bytes(raw[words.size * 8:]))
+
+
+_SEARCHERS = OrderedDict()  # set-up key -> SuperBlockSearcher (binning, sort, template, pinned inputs)
+_SEARCHER_CACHE_SIZE = 4
+
+
+def clear_setup_cache():
+    """Forget the cached super-block set-ups (binning, sort, search template, pinned copies)."""
+    _SEARCHERS.clear()
+
+
+class _SharedGrid(object):
+    """Result arrays of a multi-rank run in ONE host buffer shared by the ranks of the node
+    (a file in /dev/shm mapped by every rank and unlinked as soon as all have it): each rank
+    copies only its own z-slab from its GPU, and every rank reads the whole grid.  The part a
+    rank writes is page-locked (cudaHostRegister), so the copies are asynchronous DMA."""
+
+    def __init__(self, spec, rank, group):
+        import torch.distributed as dist
+        self.layout, off = {}, 0
+        for name, dt, n in spec:  # every array starts on a page
+            self.layout[name] = (np.dtype(dt), n, off)
+            off += -(-np.dtype(dt).itemsize * max(n, 1) // 4096) * 4096
+        self.nbytes = off
+        path = [None]
+        if rank == 0:
+            path[0] = "/dev/shm/k3d_%d_%x" % (os.getpid(), int(time.time() * 1e6) & 0xffffffff)
+            with open(path[0], "wb") as f:
+                f.truncate(self.nbytes)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast_object_list(path, src=src, group=group)
+        ok, self.map = 1, None
+        try:
+            with open(path[0], "r+b") as f:
+                self.map = mmap.mmap(f.fileno(), self.nbytes)
+        except (OSError, ValueError):
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32,
+                            device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # (also: everyone has mapped it)
+        if rank == 0:
+            os.unlink(path[0])
+        self.ok = bool(int(flag.item()))
+        self.registered = []
+        self.lent = None  # weakref to the array the last result was a view of
+        self.addr = np.frombuffer(self.map, dtype=np.uint8).ctypes.data if self.map is not None else 0
+
+    def free(self):
+        return self.lent is None or self.lent() is None
+
+    def lend(self):
+        """A fresh array over the buffer: it dies with the last result view cut from it."""
+        base = np.frombuffer(self.map, dtype=np.uint8)
+        self.lent = weakref.ref(base)
+        return base
+
+    def view(self, base, name):
+        dt, n, off = self.layout[name]
+        return base[off: off + dt.itemsize * n].view(dt)
+
+    def pin(self, name, a, b):
+        """Page-lock elements [a, b) of array `name` (whole pages around them), once."""
+        dt, n, off = self.layout[name]
+        lo = (off + a * dt.itemsize) // 4096 * 4096
+        hi = min(self.nbytes, -(-(off + b * dt.itemsize) // 4096) * 4096)
+        if hi <= lo or not torch.cuda.is_available():
+            return
+        for rlo, rhi in self.registered:
+            if rlo <= lo and hi <= rhi:
+                return
+        err = torch.cuda.cudart().cudaHostRegister(self.addr + lo, hi - lo, 0)
+        if int(err) != 0:
+            raise _native.K3dError("cudaHostRegister failed: %s" % err)
+        self.registered.append((lo, hi))
+
+    def close(self):
+        if torch.cuda.is_available():
+            for lo, hi in self.registered:
+                torch.cuda.cudart().cudaHostUnregister(self.addr + lo)
+        self.registered = []
+
+
+_SHARED = {}  # (world, rank, layout key) -> _SharedGrid
 
 
 class _MemoryData(object):
@@ -286,17 +387,34 @@ class Krige3d(object):
         return self._mdt
 
     def _create_searcher(self):
-        s = SuperBlockSearcher()
-        s.nx, s.xmn, s.xsiz = self.nx, self.xmn, self.xsiz
-        s.ny, s.ymn, s.ysiz = self.ny, self.ymn, self.ysiz
-        s.nz, s.zmn, s.zsiz = self.nz, self.zmn, self.zsiz
-        s.vr = self.vr
-        s.MAXSB = self.const.MAXSB
-        s.rotmat = self.rotmat[-1]
-        s.radsqd = self.radsqd
-        s.noct = self.noct
-        s.setup(self._device())
-        s.pickup(self._device())
+        """Super-block index of the data (krige3d.py:664-690).  Binning, the sort, the search
+        template and the pinned copies the upload reads depend only on the grid, the search
+        ellipsoid and the data: they are kept (a few set-ups, keyed by those parameters and a
+        checksum of the data bytes), so repeated runs pay for them once."""
+        vr = self.data.vr  # always the records in file order
+        dev = self._device()
+        key = (self.nx, self.xmn, self.xsiz, self.ny, self.ymn, self.ysiz, self.nz, self.zmn,
+               self.zsiz, tuple(self.const.MAXSB), self.rotmat[-1].tobytes(), self.radsqd,
+               self.noct, str(dev), data_fingerprint(vr))
+        s = _SEARCHERS.get(key)
+        if s is None:
+            s = SuperBlockSearcher()
+            s.nx, s.xmn, s.xsiz = self.nx, self.xmn, self.xsiz
+            s.ny, s.ymn, s.ysiz = self.ny, self.ymn, self.ysiz
+            s.nz, s.zmn, s.zsiz = self.nz, self.zmn, self.zsiz
+            s.vr = vr
+            s.MAXSB = self.const.MAXSB
+            s.rotmat = self.rotmat[-1]
+            s.radsqd = self.radsqd
+            s.noct = self.noct
+            s.setup(dev)
+            s.pickup(dev)
+            s.pinned = {}
+            _SEARCHERS[key] = s
+            while len(_SEARCHERS) > _SEARCHER_CACHE_SIZE:
+                _SEARCHERS.popitem(last=False)
+        else:
+            _SEARCHERS.move_to_end(key)
         self.searcher = s
         self.vr = s.vr  # sorted by super block (krige3d.py:690)
 
@@ -392,17 +510,26 @@ class Krige3d(object):
         return P
 
     def _host_inputs(self):
-        """Pinned host copies of everything the kernel reads."""
+        """Pinned host copies of everything the kernel reads (those of the sample set and its
+        index live with the cached set-up)."""
         s = self.searcher
         c = s.cols  # contiguous sorted columns
-        host = dict(
-            sx=c['x'], sy=c['y'], sz=c['z'], sv=c[self.property_name[0]],
-            ssec=c[self.property_name[1]] if (self.ktype in (2, 3)) else None,
-            sbstart=s.sbstart, runs=s.runs.reshape(-1), nodex0=s.nodex0, nodey0=s.nodey0,
-            nodez0=s.nodez0,
-            dbxyz=np.ascontiguousarray(np.concatenate([self.xdb, self.ydb, self.zdb])))
-        return {k: (None if v is None else torch.from_numpy(v).pin_memory())
-                for k, v in host.items()}
+        names = dict(sx='x', sy='y', sz='z', sv=self.property_name[0])
+        if self.ktype in (2, 3):
+            names['ssec'] = self.property_name[1]
+        host = {}
+        for k, nm in names.items():
+            if ('col', nm) not in s.pinned:
+                s.pinned[('col', nm)] = torch.from_numpy(c[nm]).pin_memory()
+            host[k] = s.pinned[('col', nm)]
+        host.setdefault('ssec', None)
+        for k in ('sbstart', 'runs', 'nodex0', 'nodey0', 'nodez0'):
+            if k not in s.pinned:
+                s.pinned[k] = torch.from_numpy(np.ascontiguousarray(getattr(s, k)).reshape(-1)).pin_memory()
+            host[k] = s.pinned[k]
+        host['dbxyz'] = torch.from_numpy(
+            np.ascontiguousarray(np.concatenate([self.xdb, self.ydb, self.zdb]))).pin_memory()
+        return host
 
     def _upload(self, host, ext_slab):
         dev = self._device()
@@ -496,14 +623,18 @@ class Krige3d(object):
             np.mean(self.xdb * self.zdb), np.mean(self.ydb * self.zdb)]) * self.resc
         self.timings['setup_s'] = time.time() - t0
 
-    def kt3d(self, neighbours=False, group=None):
+    def kt3d(self, neighbours=False, group=None, gather="host"):
         """Krige the whole grid.  Results: `estimation`, `estimation_variance` (numpy
         float64, length nx*ny*nz, x fastest, NaN = unestimated) and `status` (uint8 codes
         of include/k3d.h).  With neighbours=True also `neighbours` [nodes, ndmax] (original
         sample row numbers, nearest first, -1 padded) and `neighbour_count`.
 
         Under an initialised torch.distributed process group the grid is split into
-        z-slabs, one per rank; every rank ends up with the full arrays."""
+        z-slabs, one per rank, and every rank ends up with the full arrays.  gather="host"
+        (default): each rank copies only its own slab from its GPU, into one host buffer the
+        ranks of the node share (falls back to "device" when they do not share /dev/shm);
+        gather="device": the slabs are all-gathered between the GPUs (NCCL) and every rank
+        copies the whole grid to its host."""
         import torch.distributed as dist
         self.prepare()
         if self.koption != 0:
@@ -524,16 +655,31 @@ class Krige3d(object):
         ext_slab = None if ext is None else ext[iz0 * plane: iz1 * plane].pin_memory()
         d = self._upload(host, ext_slab)
         out = self._alloc_outputs(nodes, neighbours)
+        width = lambda k: self.ndmax if k == 'nbr_idx' else 1
+        shared = None
+        if world > 1 and gather == "host":
+            shared = self._shared_grid(out, self.nz * plane, world, rank, group)
         res = {}
-        if world == 1 and nodes > 0:
-            # one rank: the slab goes in a few runs of z-planes (cut where super blocks
-            # end), and the device-to-host copy of a run overlaps the kernels of the next
+        if world == 1 or shared is not None:
+            # The slab goes in a few runs of z-planes (cut where super blocks end), and the
+            # device-to-host copy of a run overlaps the kernels of the next.  One rank: into
+            # pooled pinned buffers; several: into the slab's place in the shared buffer.
             dev = self._device()
             main, side = torch.cuda.current_stream(dev), self._copy_stream()
-            pinned = {k: _pinned_array(v.numel(), v.dtype) for k, v in out.items()}
-            for za, zb in self._plane_runs(iz0, iz1):
+            if shared is None:
+                pinned = {k: _pinned_array(v.numel(), v.dtype) for k, v in out.items()}
+                dst = {k: pv[0] for k, pv in pinned.items()}
+                res = {k: pv[1] for k, pv in pinned.items()}
+            else:
+                base = shared.lend()
+                res = {k: shared.view(base, k) for k in out}
+                dst = {}
+                for k in out:
+                    a, b = iz0 * plane * width(k), iz1 * plane * width(k)
+                    shared.pin(k, a, b)
+                    dst[k] = torch.from_numpy(res[k][a:b])
+            for za, zb in (self._plane_runs(iz0, iz1) if nodes > 0 else []):
                 a, b = (za - iz0) * plane, (zb - iz0) * plane
-                width = lambda k: self.ndmax if k == 'nbr_idx' else 1
                 dd = dict(d)
                 if d['extgrid'] is not None:
                     dd['extgrid'] = d['extgrid'][a:b]
@@ -543,17 +689,16 @@ class Krige3d(object):
                 side.wait_event(done)
                 with torch.cuda.stream(side):
                     for k, v in out.items():
-                        pinned[k][0][a * width(k): b * width(k)].copy_(
+                        dst[k][a * width(k): b * width(k)].copy_(
                             v[a * width(k): b * width(k)], non_blocking=True)
             side.synchronize()
             main.wait_stream(side)
-            res = {k: pv[1] for k, pv in pinned.items()}
+            if shared is not None:
+                dist.barrier(group)  # every rank's slab is in place
         else:
             if nodes > 0:
                 self._launch(P, d, iz0, iz1, out)
-            if world > 1:
-                out = {k: gather_slabs(v, ranges, plane * (self.ndmax if k == 'nbr_idx' else 1), group)
-                       for k, v in out.items()}
+            out = {k: gather_slabs(v, ranges, plane * width(k), group) for k, v in out.items()}
             for k, v in out.items():
                 view, arr = _pinned_array(v.numel(), v.dtype)
                 view.copy_(v, non_blocking=True)
@@ -573,6 +718,25 @@ class Krige3d(object):
             self.neighbours_sorted_space = idx
         if self.verbose:
             print("Kriging Finished.")
+
+    def _shared_grid(self, out, total, world, rank, group):
+        """The host buffer the ranks share for results of this shape, or None when they cannot
+        share one.  A buffer is used again only when EVERY rank has let go of the arrays the
+        previous run handed out (a collective decision, so the ranks stay in step)."""
+        import torch.distributed as dist
+        spec = tuple((k, str(v.dtype).replace('torch.', ''), total * (self.ndmax if k == 'nbr_idx' else 1))
+                     for k, v in out.items())
+        key = (world, rank, id(group), spec)
+        sg = _SHARED.get(key)
+        nccl = dist.get_backend(group) == "nccl"
+        flag = torch.tensor([1 if (sg is not None and sg.free()) else 0], dtype=torch.int32,
+                            device=self._device() if nccl else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if not int(flag.item()):
+            if sg is not None:
+                sg.close()
+            sg = _SHARED[key] = _SharedGrid(spec, rank, group)
+        return sg if sg.ok else None
 
     # ------------------------------------------------------------------ option 1 / 2
     def _read_locations(self):

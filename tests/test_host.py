@@ -334,3 +334,55 @@ def test_krige2d_front_end_host_side(tmp_path):
     k3._preprocess(); k3._set_rotation()
     assert np.array_equal(k3.rotmat[-1], np.eye(3))
     assert k3.mdt == par['isk']
+
+
+_SHARED_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from pygeostatistics_b200.krige3d import _SharedGrid, slab_ranges
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+plane, nz = 100, 7
+spec = (("est", "float64", plane * nz), ("status", "uint8", plane * nz))
+sg = _SharedGrid(spec, rank, None)
+assert sg.ok and not os.path.exists("/dev/shm/k3d_%%d" %% os.getpid())
+base = sg.lend()
+a, b = slab_ranges(nz, world)[rank]
+sg.view(base, "est")[a * plane: b * plane] = rank + 1.0          # each rank writes ONLY its slab
+sg.view(base, "status")[a * plane: b * plane] = rank + 1
+dist.barrier()
+est, st = sg.view(base, "est"), sg.view(base, "status")           # ... and reads the whole grid
+for r, (ra, rb) in enumerate(slab_ranges(nz, world)):
+    assert np.all(est[ra * plane: rb * plane] == r + 1.0) and np.all(st[ra * plane: rb * plane] == r + 1)
+assert not sg.free()
+del base, est, st
+assert sg.free()                                                   # lent array gone: reusable
+if rank == 0:
+    print("SHARED_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_shared_result_buffer_two_ranks_gloo(tmp_path):
+    """The host buffer the ranks of a node share for the results of a multi-rank kt3d()."""
+    script = tmp_path / "worker.py"
+    script.write_text(_SHARED_WORKER % ROOT)
+    port = 31500 + os.getpid() % 2000
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          str(port), str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "SHARED_OK" in out.stdout
+
+
+def test_data_fingerprint_sees_edits_and_reorderings():
+    from pygeostatistics_b200.krige3d import data_fingerprint
+    rng = np.random.default_rng(0)
+    vr = np.rec.fromarrays([rng.normal(size=50) for _ in range(4)], names='x,y,z,v')
+    f0 = data_fingerprint(vr)
+    assert data_fingerprint(vr.copy()) == f0
+    e = vr.copy(); e['v'][17] = np.nextafter(e['v'][17], 1e9)
+    assert data_fingerprint(e) != f0
+    p = vr.copy(); p[[3, 9]] = p[[9, 3]]
+    assert data_fingerprint(p) != f0
