@@ -90,16 +90,24 @@ def gather_slabs(local, ranges, plane, group=None):
     return torch.cat(parts)
 
 
+_FP_WEIGHTS = {}
+
+
 def data_fingerprint(vr):
-    """Cheap checksum of a record array's bytes (sum, xor and a position-weighted sum of its
-    64-bit words): changes with any edit of a value and with any re-ordering of the rows."""
-    raw = np.ascontiguousarray(vr).view(np.uint8).reshape(-1)
-    words = raw[:raw.size // 8 * 8].view(np.uint64)
-    weights = np.arange(1, words.size + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
-    with np.errstate(over='ignore'):
-        return (vr.dtype.descr.__repr__(), int(words.size), int(words.sum(dtype=np.uint64)),
-                int(np.bitwise_xor.reduce(words)) if words.size else 0,
-                int((words * weights).sum(dtype=np.uint64)), bytes(raw[words.size * 8:]))
+    """Cheap checksum of the columns of a record array (or of a mapping name -> column): per
+    column the sum of its 64-bit words and their dot product with odd position-dependent
+    weights, modulo 2^64 -- any edit of a value and any re-ordering of the rows changes it."""
+    names = list(vr.dtype.names) if hasattr(vr, 'dtype') else list(vr.keys())
+    out = []
+    for nm in names:
+        words = np.ascontiguousarray(vr[nm], dtype=np.float64).view(np.uint64)
+        w = _FP_WEIGHTS.get(words.size)
+        if w is None:
+            _FP_WEIGHTS.clear()  # (one size at a time)
+            w = _FP_WEIGHTS[words.size] = (np.arange(words.size, dtype=np.uint64) * np.uint64(2) +
+                                           np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        out.append((nm, int(words.size), int(words.sum(dtype=np.uint64)), int(np.dot(words, w))))
+    return tuple(out)
 
 
 _SEARCHERS = OrderedDict()  # set-up key -> SuperBlockSearcher (binning, sort, template, pinned inputs)
@@ -186,7 +194,8 @@ _SHARED = {}  # (world, rank, layout key) -> _SharedGrid
 
 
 class _MemoryData(object):
-    """SpatialData look-alike over in-memory columns (same record-array layout)."""
+    """SpatialData look-alike over in-memory columns (same record-array layout, built when
+    somebody asks for it; the set-up works from the columns)."""
 
     def __init__(self, columns):
         names = list(columns.keys())
@@ -197,8 +206,16 @@ class _MemoryData(object):
         if self._2d:
             names.append('z')
             arrays.append(np.zeros_like(arrays[0]))
-        self.vr = np.rec.fromarrays(arrays, dtype=np.dtype(
-            {'names': names, 'formats': ['f8'] * len(names)}))
+        self.columns = OrderedDict(zip(names, arrays))
+        self._vr = None
+
+    @property
+    def vr(self):
+        if self._vr is None:
+            names = list(self.columns.keys())
+            self._vr = np.rec.fromarrays(list(self.columns.values()), dtype=np.dtype(
+                {'names': names, 'formats': ['f8'] * len(names)}))
+        return self._vr
 
 
 class Krige3d(object):
@@ -219,7 +236,7 @@ class Krige3d(object):
         self.locations = None      # option 1/2: (n, 3) estimated locations, file order
         self.true_values = None    # option 1/2: the value observed at each location
         self.property_name = self.data.property_name
-        self.vr = self.data.vr
+        self._vr = None
         self.rotmat = None
         self.estimation = None
         self.estimation_variance = None
@@ -306,8 +323,18 @@ class Krige3d(object):
         """(Re)load `datafl`.  The reference does this in the constructor."""
         self.data = SpatialData(self.datafl)
         self.property_name = self.data.property_name
-        self.vr = self.data.vr
+        self._vr = None
         self._2d = self.data._2d
+
+    @property
+    def vr(self):
+        """The data records: in file order until the run is prepared, then sorted by super
+        block (krige3d.py:690)."""
+        return self.data.vr if self._vr is None else self._vr
+
+    @vr.setter
+    def vr(self, value):
+        self._vr = value
 
     # ------------------------------------------------------------------ once-per-run set-up
     def _preprocess(self):
@@ -391,18 +418,21 @@ class Krige3d(object):
         template and the pinned copies the upload reads depend only on the grid, the search
         ellipsoid and the data: they are kept (a few set-ups, keyed by those parameters and a
         checksum of the data bytes), so repeated runs pay for them once."""
-        vr = self.data.vr  # always the records in file order
+        # always from the records in file order
+        cols = getattr(self.data, 'columns', None)
+        if cols is None:
+            cols = OrderedDict((nm, np.ascontiguousarray(self.data.vr[nm])) for nm in self.data.vr.dtype.names)
         dev = self._device()
         key = (self.nx, self.xmn, self.xsiz, self.ny, self.ymn, self.ysiz, self.nz, self.zmn,
                self.zsiz, tuple(self.const.MAXSB), self.rotmat[-1].tobytes(), self.radsqd,
-               self.noct, str(dev), data_fingerprint(vr))
+               self.noct, str(dev), data_fingerprint(cols))
         s = _SEARCHERS.get(key)
         if s is None:
             s = SuperBlockSearcher()
             s.nx, s.xmn, s.xsiz = self.nx, self.xmn, self.xsiz
             s.ny, s.ymn, s.ysiz = self.ny, self.ymn, self.ysiz
             s.nz, s.zmn, s.zsiz = self.nz, self.zmn, self.zsiz
-            s.vr = vr
+            s.columns = cols
             s.MAXSB = self.const.MAXSB
             s.rotmat = self.rotmat[-1]
             s.radsqd = self.radsqd

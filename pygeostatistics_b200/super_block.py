@@ -65,6 +65,7 @@ class SuperBlockSearcher(object):
         self.ny = self.ymn = self.ysiz = None
         self.nz = self.zmn = self.zsiz = None
         self.vr = None
+        self.columns = None
         self.MAXSB = []
         self.rotmat = None
         self.radsqd = None
@@ -100,8 +101,14 @@ class SuperBlockSearcher(object):
             # the reference documents at super_block.py:19-20 but does not implement)
             return np.clip(b, 0, n - 1)
 
-        names = self.vr.dtype.names
-        cols = {nm: np.ascontiguousarray(self.vr[nm]) for nm in names}
+        if getattr(self, 'columns', None) is not None:  # name -> contiguous column, file order
+            names = tuple(self.columns.keys())
+            cols = dict(self.columns)
+            rec_dtype = np.dtype({'names': list(names), 'formats': ['f8'] * len(names)})
+        else:
+            names = self.vr.dtype.names
+            cols = {nm: np.ascontiguousarray(self.vr[nm]) for nm in names}
+            rec_dtype = self.vr.dtype
         bx = bins(self.xmnsup, self.xsizsup, self.nxsup, cols['x'])
         by = bins(self.ymnsup, self.ysizsup, self.nysup, cols['y'])
         bz = bins(self.zmnsup, self.zsizsup, self.nzsup, cols['z'])
@@ -117,7 +124,7 @@ class SuperBlockSearcher(object):
         # sorted columns (contiguous: what the device upload takes) and the sorted record
         # array the reference exposes (krige3d.py:690)
         self.cols = {nm: c[self.sort_index] for nm, c in cols.items()}
-        self.vr = np.rec.fromarrays([self.cols[nm] for nm in names], dtype=self.vr.dtype)
+        self.vr = np.rec.fromarrays([self.cols[nm] for nm in names], dtype=rec_dtype)
         counts = np.bincount(blk, minlength=nsup)
         self.nisb = np.cumsum(counts, dtype=np.int64)
         self.sbstart = np.concatenate([[0], self.nisb]).astype(np.int32)
