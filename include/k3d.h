@@ -92,6 +92,13 @@ typedef struct K3dParams {
     int32_t nxsup, nysup, nzsup;
     /* block discretisation: ndb joint points (krige3d.py:692-707) */
     int32_t ndb;
+    /* work decomposition, not semantics: a CTA works on a brick of brick[0] x brick[1] x
+       brick[2] super blocks (0 or 1 = one super block).  K3dInputs.runs / ntmpl must then
+       describe the union of the templates of the brick's blocks, relative to its first
+       block.  Useful when super blocks hold only a few grid nodes; results do not change
+       (every sample within the search radius is in the template of its node's block). */
+    int32_t brick[3];
+    int32_t _pad3;
 } K3dParams;
 
 /*

@@ -33,6 +33,7 @@ class K3dParams(C.Structure):
         ("maxcov", C.c_double), ("resc", C.c_double), ("unbias", C.c_double), ("cbb", C.c_double),
         ("bv", C.c_double * MAXDRIFT),
         ("nxsup", C.c_int32), ("nysup", C.c_int32), ("nzsup", C.c_int32), ("ndb", C.c_int32),
+        ("brick", C.c_int32 * 3), ("_pad3", C.c_int32),
     ]
 
 

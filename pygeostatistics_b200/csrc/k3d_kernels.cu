@@ -569,13 +569,21 @@ struct PtSet {
 __device__ __forceinline__ Tile tile_of_block(const K3dParams &P, const K3dInputs &in, int iz0,
                                               int iz1, const PtSet &pts, int tile0)
 {
+    // A tile is a BRICK of brick[0] x brick[1] x brick[2] super blocks (1 x 1 x 1 unless the
+    // caller asks for more: super blocks of a few nodes make CTAs too small); the template
+    // runs the caller passes are then those of the whole brick, relative to its first block.
     Tile T;
+    const int bx = P.brick[0] > 1 ? P.brick[0] : 1, by = P.brick[1] > 1 ? P.brick[1] : 1,
+              bz = P.brick[2] > 1 ? P.brick[2] : 1;
+    const int nbx = (P.nxsup + bx - 1) / bx, nby = (P.nysup + by - 1) / by;
     int tile = blockIdx.x + tile0;
     const int tile_id = tile;
-    T.sbx = tile % P.nxsup;
-    tile /= P.nxsup;
-    T.sby = tile % P.nysup;
-    T.sbz = tile / P.nysup;
+    T.sbx = (tile % nbx) * bx;
+    tile /= nbx;
+    T.sby = (tile % nby) * by;
+    T.sbz = (tile / nby) * bz;
+    const int sbx1 = min(T.sbx + bx, P.nxsup), sby1 = min(T.sby + by, P.nysup),
+              sbz1 = min(T.sbz + bz, P.nzsup);
     T.x0 = in.nodex0[T.sbx];
     T.y0 = in.nodey0[T.sby];
     T.zsb0 = in.nodez0[T.sbz];
@@ -587,11 +595,11 @@ __device__ __forceinline__ Tile tile_of_block(const K3dParams &P, const K3dInput
         T.tnx = T.tny = T.tnz = 1;
         return T;
     }
-    int z1 = in.nodez0[T.sbz + 1];
+    int z1 = in.nodez0[sbz1];
     T.z0 = T.zsb0 > iz0 ? T.zsb0 : iz0;
     z1 = z1 < iz1 ? z1 : iz1;
-    T.tnx = in.nodex0[T.sbx + 1] - T.x0;
-    T.tny = in.nodey0[T.sby + 1] - T.y0;
+    T.tnx = in.nodex0[sbx1] - T.x0;
+    T.tny = in.nodey0[sby1] - T.y0;
     T.tnz = z1 - T.z0;
     T.tnodes = (T.tnx > 0 && T.tny > 0 && T.tnz > 0) ? T.tnx * T.tny * T.tnz : 0;
     return T;
@@ -1624,6 +1632,34 @@ __global__ void k3d_dfma_probe(double *sink, int iters)
     if (s == 123.456) sink[0] = s;
 }
 
+// The same pipe with the operand pattern of the elimination's rank-1 update: 5 x 5 accumulators,
+// every DFMA reading three distinct register pairs (m += w[a] * u[b]).
+__global__ void k3d_dfma_rank1_probe(double *sink, int iters)
+{
+    double m[5][5], w[5], u[5];
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+        w[a] = 1.0 + (threadIdx.x + a) * 1e-9;
+        u[a] = 1e-7 * (1 + a);
+#pragma unroll
+        for (int b = 0; b < 5; b++) m[a][b] = a + b;
+    }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int a = 0; a < 5; a++)
+#pragma unroll
+            for (int b = 0; b < 5; b++) m[a][b] = fma(w[a], u[b], m[a][b]);
+#pragma unroll
+        for (int a = 0; a < 5; a++) { w[a] += 1e-12; u[a] -= 1e-13; } // keeps the loop from folding
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < 5; a++)
+#pragma unroll
+        for (int b = 0; b < 5; b++) s += m[a][b];
+    if (s == 123.456) sink[0] = s;
+}
+
 // ---------------------------------------------------------------------------
 // self test of the in-line math (exp_neg, sqrt_pos, rcp_fast) against the CUDA library
 // ---------------------------------------------------------------------------
@@ -1760,7 +1796,7 @@ int make_scfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_
 }
 
 // ---- solve kernel plan: warps per CTA and CTAs per SM -------------------------------------
-int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
+int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, int static_smem, BCfg *c)
 {
     memset(c, 0, sizeof(*c));
     c->rtot = p->ndmax + p->mdt + 2;
@@ -1807,15 +1843,18 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, BCfg *c)
         const int ctas = shapes[i][0], warps = shapes[i][1];
         if (warps > max_cta_warps || ctas * warps > max_sm_warps) continue;
         if (force_warps && (ctas != force_ctas || warps != force_warps)) continue;
-        // the driver reserves 1 KB per CTA; 1.5 KB covers the kernel's static shared memory
-        const int budget = (smem_max + 1024) / ctas - 1024 - 1536;
+        // the driver reserves 1 KB per CTA, and the kernel has its static shared memory
+        const int budget = (smem_max + 1024) / ctas - 1024 - static_smem;
         c->warps = warps;
         const int bytes = b_off_warp(*c) + warps * bpw_bytes(*c);
         if (bytes > budget) continue;
-        // (measured on c3/c4: CTAs of 2-4 warps lose 5-10 % to the imbalance of a small
-        // covariance pool, whatever their number per SM)
+        // Measured on c3 / c4 / c5: resident warps count most; a walk
+        // longer than ~13 nodes adds little; a single CTA per SM loses ~10 % (nothing runs
+        // while it waits at its phase barriers); CTAs of 2-3 warps lose 10-15 % to the
+        // imbalance of a small covariance pool.
         const double per = tile_nodes / warps;
-        const double score = ctas * warps * per / (per + 4.0) * warps / (warps + 2.0);
+        const double score = ctas * warps * per / (per + 1.5) * (ctas == 1 ? 0.88 : 1.0) *
+                             (warps <= 2 ? 0.85 : warps == 3 ? 0.8 : warps == 4 ? 0.97 : 1.0);
         if (score > best) {
             best = score;
             c->pw_bytes = bpw_bytes(*c);
@@ -1900,6 +1939,24 @@ int launch_solve(const K3dParams *p, const KPrep *q, const K3dInputs *in, const 
                       : launch_solve2<AMAX, false>(p, q, in, out, iz0, iz1, nbr, cnt, c, tile0, ntiles, st, ps);
 }
 
+// static shared memory of the solve kernel instantiation a run will use
+template <int AMAX>
+size_t solve_static_smem_of(bool block)
+{
+    cudaFuncAttributes fa;
+    const void *f = block ? (const void *)k3d_solve_kernel<AMAX, true> : (const void *)k3d_solve_kernel<AMAX, false>;
+    return cudaFuncGetAttributes(&fa, f) == cudaSuccess ? fa.sharedSizeBytes : 1536;
+}
+int solve_static_smem(int amax, bool block)
+{
+    switch (amax) {
+    case 5: return (int)solve_static_smem_of<5>(block);
+    case 9: return (int)solve_static_smem_of<9>(block);
+    case 11: return (int)solve_static_smem_of<11>(block);
+    default: return (int)solve_static_smem_of<0>(block);
+    }
+}
+
 template <bool PTS, bool OCT>
 int launch_search(const K3dParams *p, const K3dInputs *in, int iz0, int iz1, int tile0,
                   long long ntiles, int32_t *nbr, int32_t *cnt, int32_t *ncand, int ordered,
@@ -1957,6 +2014,9 @@ static int validate(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32_
     }
     if (!(p->radsqd > 0.0)) return fail(K3D_EINVAL, "search radius must be positive");
     if (p->mdt < 0 || p->mdt > K3D_MAXDRIFT + 2) return fail(K3D_EINVAL, "bad mdt");
+    for (int i = 0; i < 3; i++)
+        if (p->brick[i] < 0 || p->brick[i] > 8 || (points && p->brick[i] > 1))
+            return fail(K3D_EINVAL, "brick outside 0..8 (and 1 for listed locations)");
     if (!in->sx || !in->sy || !in->sz || !in->sv || !in->sbstart || !in->runs ||
         !in->nodex0 || !in->nodey0 || !in->nodez0 || !in->dbxyz)
         return fail(K3D_EINVAL, "NULL input array");
@@ -1989,16 +2049,21 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
     int dev = 0, smem_max = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const double nsb = (double)p->nxsup * p->nysup * p->nzsup;
+    const int bkx = p->brick[0] > 1 ? p->brick[0] : 1, bky = p->brick[1] > 1 ? p->brick[1] : 1,
+              bkz = p->brick[2] > 1 ? p->brick[2] : 1;
+    const int nbx = (p->nxsup + bkx - 1) / bkx, nby = (p->nysup + bky - 1) / bky,
+              nbz = (p->nzsup + bkz - 1) / bkz;
+    const double nsb = (double)p->nxsup * p->nysup * p->nzsup, ntl_all = (double)nbx * nby * nbz;
+    // (ntmpl counts the super blocks a TILE searches: the brick's template when bricks are used)
     const double mean_cand = in->ntmpl > 0 ? (double)in->nd / nsb * in->ntmpl : 512.0;
-    const double tile_nodes = pts ? (double)pts->npts / nsb : (double)p->nx * p->ny * p->nz / nsb;
+    const double tile_nodes = pts ? (double)pts->npts / nsb : (double)p->nx * p->ny * p->nz / ntl_all;
     SCfg sc;
     BCfg bc;
     if (make_scfg(p, mean_cand, tile_nodes, smem_max, &sc) != K3D_OK ||
-        make_bcfg(p, tile_nodes, smem_max, &bc) != K3D_OK)
+        make_bcfg(p, tile_nodes, smem_max, solve_static_smem(amax_for(p->ndmax + p->mdt + 2), p->ndb > 1), &bc) != K3D_OK)
         return fail(K3D_ECAPACITY, "ndmax/drift/discretisation exceed the shared memory of an SM");
     // one CTA per super block; CTAs whose super block does not meet the planes exit at once
-    const long long ntiles = (long long)p->nxsup * p->nysup * p->nzsup;
+    const long long ntiles = (long long)nbx * nby * nbz;
     if (ntiles > 0x7fffffffLL) return fail(K3D_EINVAL, "too many tiles");
     KPrep q;
     make_prep(p, &q);
@@ -2067,8 +2132,10 @@ static int krige_run(const K3dParams *p, const K3dInputs *in, int32_t iz0, int32
             int l1 = (int)((double)(zb - 1) * p->nzsup / p->nz) + 1;
             l0 = l0 < 0 ? 0 : l0;
             l1 = l1 >= p->nzsup ? p->nzsup - 1 : l1;
-            tile0 = l0 * p->nxsup * p->nysup;
-            ntl = (long long)(l1 - l0 + 1) * p->nxsup * p->nysup;
+            l0 /= bkz; // (layers of bricks)
+            l1 /= bkz;
+            tile0 = l0 * nbx * nby;
+            ntl = (long long)(l1 - l0 + 1) * nbx * nby;
         }
         const int sz0 = pts ? 0 : za, sz1 = pts ? p->nz : zb, ordered = co.nbr_idx ? 1 : 0;
         cudaEventRecord(g_ev[0], st);
@@ -2159,6 +2226,23 @@ int k3d_measure_fp64_peak(double *tflops, double *ms, void *stream)
     double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
     *tflops = flops / (best * 1e-3) / 1e12;
     if (ms) *ms = best;
+    if (getenv("K3D_PROBE_RANK1")) { // diagnostic: the update's operand pattern (35 flop-instr / iteration)
+        const int it2 = 1 << 14;
+        k3d_dfma_rank1_probe<<<blocks, threads, 0, st>>>(sink, 256);
+        float b2 = 1e30f;
+        for (int rep = 0; rep < 5; rep++) {
+            cudaEventRecord(e0, st);
+            k3d_dfma_rank1_probe<<<blocks, threads, 0, st>>>(sink, it2);
+            cudaEventRecord(e1, st);
+            cudaEventSynchronize(e1);
+            float t = 0;
+            cudaEventElapsedTime(&t, e0, e1);
+            if (t < b2) b2 = t;
+        }
+        fprintf(stderr, "k3d rank-1 DFMA pattern: %.2f TFLOP/s counting the 25 FMAs (35 fp64 instructions per iteration: %.2f T-instr/s x2)\n",
+                2.0 * 25.0 * it2 * blocks * threads / (b2 * 1e-3) / 1e12,
+                2.0 * 35.0 * it2 * blocks * threads / (b2 * 1e-3) / 1e12);
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);

@@ -29,7 +29,7 @@ import torch
 from . import _native
 from .gslib_io import (SpatialData, read_params, read_grid_column, write_gslib_grid,
                        write_gslib_validation)
-from .super_block import SuperBlockSearcher
+from .super_block import SuperBlockSearcher, brick_template
 
 EPS = np.finfo(float).eps
 
@@ -255,6 +255,7 @@ class Krige3d(object):
         self.verbose = True
         self.timings = {}
         self._dev = None
+        self.brick_size = None         # (bx, by, bz) super blocks per CTA tile; None = automatic
         self.search_identity = False   # Krige2d: isotropic search with the exact identity matrix
         self.flags = 0                 # K3dParams.flags (include/k3d.h)
 
@@ -537,7 +538,29 @@ class Krige3d(object):
             P.bv[i] = self.bv[i]
         s = self.searcher
         P.nxsup, P.nysup, P.nzsup, P.ndb = s.nxsup, s.nysup, s.nzsup, self.ndb
+        for i, b in enumerate(self._brick()):
+            P.brick[i] = b
         return P
+
+    def _brick(self):
+        """Super blocks per CTA tile and axis.  The reference sizes super blocks by the grid
+        (at most 50 per axis, krige3d.py:164-170), so a small grid gets super blocks of a
+        few nodes; CTAs then work on bricks of 2-4 blocks per axis (about 64 nodes or
+        more), searching the union of their templates.  Grid runs only."""
+        s = self.searcher
+        if self.koption != 0:
+            return (1, 1, 1)
+        if self.brick_size is not None:
+            return tuple(int(min(max(v, 1), n, 8)) for v, n in
+                         zip(self.brick_size, (s.nxsup, s.nysup, s.nzsup)))
+        tile = self.nx * self.ny * self.nz / float(s.nxsup * s.nysup * s.nzsup)
+        if tile >= 48:
+            return (1, 1, 1)
+        for b in (2, 3, 4):
+            dims = tuple(min(b, n) for n in (s.nxsup, s.nysup, s.nzsup))
+            if tile * dims[0] * dims[1] * dims[2] >= 64:
+                break
+        return dims
 
     def _host_inputs(self):
         """Pinned host copies of everything the kernel reads (those of the sample set and its
@@ -553,10 +576,17 @@ class Krige3d(object):
                 s.pinned[('col', nm)] = torch.from_numpy(c[nm]).pin_memory()
             host[k] = s.pinned[('col', nm)]
         host.setdefault('ssec', None)
-        for k in ('sbstart', 'runs', 'nodex0', 'nodey0', 'nodez0'):
+        for k in ('sbstart', 'nodex0', 'nodey0', 'nodez0'):
             if k not in s.pinned:
                 s.pinned[k] = torch.from_numpy(np.ascontiguousarray(getattr(s, k)).reshape(-1)).pin_memory()
             host[k] = s.pinned[k]
+        brick = self._brick()
+        if ('runs', brick) not in s.pinned:  # the template of a tile (a brick of super blocks)
+            runs, ntmpl = (s.runs, s.nsbtosr) if brick == (1, 1, 1) else \
+                brick_template(s.ixsbtosr, s.iysbtosr, s.izsbtosr, brick)
+            s.pinned[('runs', brick)] = (torch.from_numpy(np.ascontiguousarray(runs).reshape(-1)).pin_memory(),
+                                         int(ntmpl))
+        host['runs'], self._ntmpl = s.pinned[('runs', brick)]
         host['dbxyz'] = torch.from_numpy(
             np.ascontiguousarray(np.concatenate([self.xdb, self.ydb, self.zdb]))).pin_memory()
         return host
@@ -574,7 +604,7 @@ class Krige3d(object):
         I.sx, I.sy, I.sz, I.sv, I.ssec = ptr(d['sx']), ptr(d['sy']), ptr(d['sz']), ptr(d['sv']), \
             ptr(d['ssec'])
         I.sbstart, I.nruns, I.runs = ptr(d['sbstart']), int(d['runs'].numel() // 4), ptr(d['runs'])
-        I.ntmpl = int(self.searcher.nsbtosr)
+        I.ntmpl = int(getattr(self, '_ntmpl', None) or self.searcher.nsbtosr)
         I.nodex0, I.nodey0, I.nodez0 = ptr(d['nodex0']), ptr(d['nodey0']), ptr(d['nodez0'])
         I.dbxyz, I.extgrid = ptr(d['dbxyz']), ptr(d['extgrid'])
         return I

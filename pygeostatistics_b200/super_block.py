@@ -191,6 +191,18 @@ class SuperBlockSearcher(object):
         self.runs = template_runs(m, self.nxsup, self.nysup, self.nzsup)
 
 
+def brick_template(dx, dy, dz, brick):
+    """Template of a brick of brick[0] x brick[1] x brick[2] super blocks, relative to its
+    first block: the union of the single-block template shifted to each block of the brick.
+    Returns (runs, number of offsets)."""
+    off = np.stack([np.asarray(a, dtype=np.int64) for a in (dx, dy, dz)], axis=1)
+    i, j, k = np.meshgrid(np.arange(brick[0]), np.arange(brick[1]), np.arange(brick[2]),
+                          indexing='ij')
+    shifts = np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1)
+    allo = np.unique((off[:, None, :] + shifts[None, :, :]).reshape(-1, 3), axis=0)
+    return runs_from_offsets(allo[:, 0], allo[:, 1], allo[:, 2]), int(allo.shape[0])
+
+
 def runs_from_offsets(dx, dy, dz):
     """Same runs as template_runs, from the offset lists: sort by (dz, dy, dx) and cut
     wherever dx stops being consecutive."""

@@ -288,6 +288,7 @@ def test_host_buffer_c_abi_entry():
     from pygeostatistics_b200 import Krige3d, _native
     par, data, sec = k3d_configs.config("c3", 0.12)
     k = gpu_run(par, data, sec)
+    k.brick_size = (1, 1, 1)    # the hand-made inputs below carry the one-block template
     P = k._params_struct()
     s = k.searcher
     arrs = dict(sx=np.ascontiguousarray(k.vr['x']), sy=np.ascontiguousarray(k.vr['y']),

@@ -232,6 +232,7 @@ def test_c_abi_error_codes():
     assert L.k3d_selftest_math(0, None, None, stream) == EINVAL
     # K3D_ENOMEM: a host-buffer call whose device arena cannot be allocated (nothing is
     # copied before the allocation succeeds)
+    k.brick_size = (1, 1, 1)
     P = k._params_struct()
     P.nx = P.ny = P.nz = 1 << 15
     s = k.searcher
@@ -286,3 +287,31 @@ def test_largest_supported_system():
     assert np.array_equal(np.isnan(k.estimation), np.isnan(est))
     ok = ~np.isnan(est)
     assert np.allclose(k.estimation[ok], est[ok], rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("brick", [(2, 2, 2), (3, 2, 1), (4, 4, 4), (8, 1, 3)])
+def test_bricks_of_super_blocks(brick):
+    """A CTA tile may be a brick of super blocks searching the union of their templates (used
+    automatically when super blocks hold few nodes): same neighbours, same estimates."""
+    from pygeostatistics_b200 import Krige3d
+    for name, scale in (("c3", 0.2), ("c2", 0.3)):
+        par, data, sec = k3d_configs.config(name, scale)
+        st, ores = oracle_run(par, data, sec)
+        k = Krige3d(par, data=data, secondary=sec)
+        k.verbose = False
+        k.brick_size = brick
+        k.kt3d(neighbours=True)
+        assert k._brick() == tuple(min(b, n) for b, n in
+                                   zip(brick, (k.searcher.nxsup, k.searcher.nysup, k.searcher.nzsup)))
+        compare(k, st, ores, vmax=float(np.max(np.abs(data['v']))))
+
+
+def test_automatic_bricks_for_small_super_blocks():
+    par, data, sec = k3d_configs.config("c2", 1.0)    # super blocks of 2.56^3 nodes
+    k = gpu_run(par, data, sec, neighbours=False)
+    assert k._brick() == (2, 2, 2)
+    par3, data3, sec3 = k3d_configs.config("c3", 1.0)  # 5.12^3: one block per tile
+    from pygeostatistics_b200 import Krige3d
+    k3 = Krige3d(par3, data=data3)
+    k3.prepare()
+    assert k3._brick() == (1, 1, 1)
