@@ -381,7 +381,7 @@ def main():
         sync_all()
 
     extra_c5 = None
-    if (args.also_c5 or world == 8) and args.config != "c5":
+    if (args.also_c5 or world == 8) and args.config != "c5" and not os.environ.get("K3D_BENCH_NO_C5"):
         c5 = device_timed("c5", 1.0, max(2, min(args.steps, 3)), 3, world, rank, dev, with_stats=False)
         extra_c5 = {"metric": METRIC, "value": c5['value'], "unit": UNIT, "n_gpus": world,
                     "ms_per_step": c5['step_ms'] / max(2, min(args.steps, 3)),

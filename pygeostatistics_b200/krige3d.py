@@ -143,14 +143,20 @@ class _SharedGrid(object):
         try:
             with open(path[0], "r+b") as f:
                 self.map = mmap.mmap(f.fileno(), self.nbytes)
-        except (OSError, ValueError):
+        except (OSError, ValueError) as e:
             ok = 0
+            if os.environ.get("K3D_DEBUG"):
+                print("k3d: rank %d cannot map %r: %r" % (rank, path[0], e), flush=True)
         flag = torch.tensor([ok], dtype=torch.int32,
                             device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # (also: everyone has mapped it)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        # reading the result is what makes the host wait (NCCL only queues the reduction):
+        # after it every rank has mapped the file, and the name can go
+        self.ok = bool(int(flag.item()))
         if rank == 0:
             os.unlink(path[0])
-        self.ok = bool(int(flag.item()))
+        if os.environ.get("K3D_DEBUG"):
+            print("k3d: rank %d shared grid %r local ok %d, all ok %d" % (rank, path[0], ok, self.ok), flush=True)
         self.registered = []
         self.lent = None  # weakref to the array the last result was a view of
         self.addr = np.frombuffer(self.map, dtype=np.uint8).ctypes.data if self.map is not None else 0
@@ -653,9 +659,11 @@ class Krige3d(object):
             Krige3d._COPY_STREAMS[dev] = torch.cuda.Stream(dev)
         return Krige3d._COPY_STREAMS[dev]
 
-    def _plane_runs(self, iz0, iz1, target=4):
+    def _plane_runs(self, iz0, iz1, target=None):
         """[iz0, iz1) cut into about `target` runs of z-planes at super-block boundaries (a
         run that splits a super block would shorten the walks of its tiles)."""
+        if target is None:
+            target = int(os.environ.get("K3D_PLANE_RUNS", "4"))
         starts = [int(z) for z in self.searcher.nodez0 if iz0 < z < iz1]
         want = [iz0 + (iz1 - iz0) * j // target for j in range(1, target)]
         cuts = sorted({min(starts, key=lambda z: abs(z - w)) for w in want}) if starts else []
@@ -717,8 +725,11 @@ class Krige3d(object):
         out = self._alloc_outputs(nodes, neighbours)
         width = lambda k: self.ndmax if k == 'nbr_idx' else 1
         shared = None
+        tm = self.timings
+        tm['upload_s'] = time.time() - t0
         if world > 1 and gather == "host":
             shared = self._shared_grid(out, self.nz * plane, world, rank, group)
+        tm['shared_s'] = time.time() - t0 - tm['upload_s']
         res = {}
         if world == 1 or shared is not None:
             # The slab goes in a few runs of z-planes (cut where super blocks end), and the
@@ -751,10 +762,14 @@ class Krige3d(object):
                     for k, v in out.items():
                         dst[k][a * width(k): b * width(k)].copy_(
                             v[a * width(k): b * width(k)], non_blocking=True)
+            tm['launch_s'] = time.time() - t0 - tm['upload_s'] - tm['shared_s']
             side.synchronize()
             main.wait_stream(side)
+            tm['device_wait_s'] = time.time() - t0 - tm['upload_s'] - tm['shared_s'] - tm['launch_s']
             if shared is not None:
+                t1 = time.time()
                 dist.barrier(group)  # every rank's slab is in place
+                tm['barrier_s'] = time.time() - t1
         else:
             if nodes > 0:
                 self._launch(P, d, iz0, iz1, out)
