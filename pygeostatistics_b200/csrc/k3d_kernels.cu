@@ -58,6 +58,13 @@
 // measured as the difference between 2.5 and 0.2 "no instruction" stall cycles per issue.
 #define K3D_PHASE_BARRIER() __syncthreads()
 
+#ifdef K3D_PHASE_CLOCKS /* diagnostic build: cycles a warp spends in each phase of the solve kernel */
+__device__ unsigned long long g_phase_clk[8];
+#define K3D_CLK(i) do { const long long c_ = clock64(); if (lane == 0) pc_[i] += c_ - pt_; pt_ = c_; } while (0)
+#else
+#define K3D_CLK(i) do { } while (0)
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -1241,6 +1248,9 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     const int t_begin = warp * per, t_end = (t_begin + per < T.tnodes) ? t_begin + per : T.tnodes;
     int nprev = -1; // neighbours of the previous node whose covariances are still in Pm
 
+#ifdef K3D_PHASE_CLOCKS
+    long long pc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt_ = clock64();
+#endif
     for (int tt = 0; tt < per; tt++) {
         const int t = t_begin + tt;
         const bool active = t < t_end;
@@ -1376,7 +1386,9 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             }
         }
         if (tid == 0) s_nrounds[(tt + 1) & 1] = 0; // next node's counter: idle during this phase
+        K3D_CLK(0); // match / fill / publish
         K3D_PHASE_BARRIER();
+        K3D_CLK(1); // barrier 1
 
         // ---- 2. covariances of every node in flight, pooled over the CTA ---------------
         // One work loop evaluates every covariance the nodes need (krige3d.py:748-801,
@@ -1466,7 +1478,9 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     sts_f64(jb + (pk(jR - p1, rhs ? 1 : jR - p2r) << 3), acc);
             }
         }
+        K3D_CLK(2); // covariance rounds
         K3D_PHASE_BARRIER();
+        K3D_CLK(3); // barrier 2
         if (solve) {
             if (na == 1) { // krige3d.py:423-468 (mdt == 0 here, R == 2)
                 double cb = Pm[pk(R, 1)];
@@ -1552,6 +1566,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 if (P.ktype == 3 && lane == 0) Pm[pk(R - (N - 1), 1)] = extest * resce; // last constraint
                 __syncwarp();
 
+                K3D_CLK(4); // border
                 // ---- 3. LDL^T elimination of the N pivots ---------------------------
                 unsigned minhi;
                 if constexpr (AMAX > 0) {
@@ -1573,6 +1588,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 __syncwarp();
             }
         }
+        K3D_CLK(5); // elimination
         if (lane == 0 && active) {
             out.est[o] = est;
             out.var[o] = var;
@@ -1580,6 +1596,10 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
         }
         __syncwarp();
     }
+#ifdef K3D_PHASE_CLOCKS
+    if (lane == 0)
+        for (int i = 0; i < 8; i++) atomicAdd(&g_phase_clk[i], (unsigned long long)pc_[i]);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -1986,6 +2006,18 @@ const char *k3d_last_error(void) { return g_err; }
 int k3d_last_launch(K3dLaunchInfo *info)
 {
     if (!info) return fail(K3D_EINVAL, "info is NULL");
+#ifdef K3D_PHASE_CLOCKS
+    {
+        unsigned long long h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_phase_clk, sizeof(h));
+        cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
+        double tot = 0;
+        for (int i = 0; i < 6; i++) tot += (double)h[i];
+        static const char *nm[6] = {"fill", "barrier1", "cov", "barrier2", "border", "ldl+out"};
+        for (int i = 0; i < 6; i++) fprintf(stderr, "phase %-9s %5.1f %%\n", nm[i], 100.0 * h[i] / (tot > 0 ? tot : 1));
+    }
+#endif
     if (g_ev_pending) {
         g_ev_pending = false;
         if (cudaEventSynchronize(g_ev[2]) == cudaSuccess) {
