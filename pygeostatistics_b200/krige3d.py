@@ -20,6 +20,7 @@ import ctypes as C
 import mmap
 import os
 import time
+import warnings
 import weakref
 from collections import OrderedDict, namedtuple
 
@@ -307,6 +308,8 @@ class Krige3d(object):
                 raise ValueError("INVALID variogram number {}".format(vtype))
             if vtype == 4 and (a_range < 0 or a_range > 2.0):
                 raise ValueError("INVALID power variogram")
+            if vtype != 4 and not a_range > 0:  # (the reference divides by it: inf / nan everywhere)
+                raise ValueError("variogram range aa_hmax must be positive")
         if self.ktype == 3 and self.iextv <= 0:
             raise ValueError("Must have exteranl variable")
         if self.ixl < 0 and self.nx > 1:
@@ -839,11 +842,25 @@ class Krige3d(object):
     def _kt3d_locations(self, neighbours=False):
         """Cross-validation / jackknife: the same two kernels, with the listed locations
         grouped by super block in place of the grid nodes (k3d_krige_points).  Every rank of
-        a process group computes all locations (these runs are small)."""
+        a process group computes all locations (these runs are small).  Locations outside
+        the grid extent are searched from the nearest edge super block -- a warning says how
+        many (`locations_outside_grid`): inside the grid the template of a location's block
+        holds every sample within the radius, outside it need not."""
         t0 = time.time()
         x, y, z, true, ext = self._read_locations()
         n = x.shape[0]
         s = self.searcher
+        outside = ((x < self.xmn - 0.5 * self.xsiz) | (x > self.xmn + (self.nx - 0.5) * self.xsiz) |
+                   (y < self.ymn - 0.5 * self.ysiz) | (y > self.ymn + (self.ny - 0.5) * self.ysiz) |
+                   (z < self.zmn - 0.5 * self.zsiz) | (z > self.zmn + (self.nz - 0.5) * self.zsiz))
+        self.locations_outside_grid = int(np.count_nonzero(outside))
+        if self.locations_outside_grid:
+            # such a location is searched from the nearest edge super block (the reference's
+            # getindx has no defined answer for it): samples within the radius of the location
+            # but outside that block's template are not seen
+            warnings.warn("%d of %d locations lie outside the grid extent; their neighbourhoods "
+                          "are those of the nearest edge super block and may miss samples"
+                          % (self.locations_outside_grid, n))
         blk = s.block_of_locations(x, y, z)
         order = np.argsort(blk, kind='stable')
         nsup = s.nxsup * s.nysup * s.nzsup

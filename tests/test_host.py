@@ -63,7 +63,8 @@ def test_param_file_and_checks(tmp_path):
     for bad, exc in ((dict(radius_hmax=0), ValueError), (dict(nst=0), ValueError),
                      (dict(it=[7]), ValueError), (dict(it=[4], aa_hmax=[2.5]), ValueError),
                      (dict(idrift=[0] * 9), ValueError), (dict(ikrige=3, icolsec=0), ValueError),
-                     (dict(ndmax=65), ValueError), (dict(option=3), ValueError)):
+                     (dict(ndmax=65), ValueError), (dict(option=3), ValueError),
+                     (dict(aa_hmax=[0.0]), ValueError)):
         with pytest.raises(exc):
             Krige3d(dict(par, **bad), data={'x': np.zeros(2), 'y': np.zeros(2), 'v': np.zeros(2)})
     missing = dict(par)
