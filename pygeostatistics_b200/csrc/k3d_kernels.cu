@@ -159,8 +159,8 @@ __host__ __device__ inline int s_off_red(const SCfg &c) { return align16(s_off_b
 __host__ __device__ inline int s_off_warp(const SCfg &c) { return align16(s_off_red(c) + 8 * 6 * 8); }
 __host__ __device__ inline int spw_bytes(const SCfg &c)
 {
-    const int E = c.nlist * c.cap; // (8 bounds per lane: octants, or the groups of the one list)
-    return align16(E * 384 + 8 * 256 + 8 * 64);
+    const int E = c.nlist * c.cap;
+    return align16(E * 320 + (c.nlist == 8 ? 0 : 8 * 256) + 8 * 64);
 }
 __host__ __device__ inline int s_total_bytes(const SCfg &c)
 {
@@ -879,17 +879,36 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
     const int nsorted = staged ? (int)bstart[K3D_SBINS] : 0;
 
     // ---- 4. one thread per node: stream the candidates, keep the nearest ------------------
+    // An entry is a distance (f64) and a 16-bit reference: the candidate's place in the
+    // sorted stage (bit 15: the sample at the location itself).  A tile that walks global
+    // memory has no stage: its references are sample indices (bit 31: the flag) whose upper
+    // halves go where the stage would have been.
     const int cap = cfg.cap, nlist = OCT ? 8 : 1, E = nlist * cap;
-    double *keys = (double *)(wreg + warp * cfg.pw_bytes); // [E][32] distances
-    int *gidx = (int *)((unsigned char *)keys + E * 256);  // [E][32] sample index (bit 31: the
-                                                           //  sample at the location itself)
-    double *tau = (double *)((unsigned char *)keys + E * 384);          // [nlist][32] farthest kept
-    unsigned short *count = (unsigned short *)((unsigned char *)tau + 8 * 256);       // [8][32]
+    const bool cnt_reg = OCT && cap <= 15;   // octant counts: 4 bits each in one register
+    double *keys = (double *)(wreg + warp * cfg.pw_bytes);                        // [E][32] distances
+    unsigned short *ref = (unsigned short *)((unsigned char *)keys + E * 256);    // [E][32] references
+    unsigned short *refhi = (unsigned short *)smem + warp * (E * 32);             // (no stage) upper halves
+    double *tau = (double *)((unsigned char *)keys + E * 320);         // [8][32] bounds (see spw_bytes)
+    unsigned short *count = (unsigned short *)((unsigned char *)tau + (OCT ? 0 : 8 * 256)); // [8][32]
     unsigned *outl = (unsigned *)keys; // [ndmax][33] output staging, once the keys are dead
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const unsigned GM = 0x7fffffffu;
     const size_t slab_off = (size_t)iz0 * P.nx * P.ny;
     const int excl = PTS ? pts.exclude : 0;
+    const unsigned FLAG = staged ? 0x8000u : 0x80000000u;
+    auto ref_get = [&](int row) -> unsigned {
+        unsigned v = ref[row * 32 + lane];
+        if (!staged) v |= (unsigned)refhi[row * 32 + lane] << 16;
+        return v;
+    };
+    auto ref_put = [&](int row, unsigned v) {
+        ref[row * 32 + lane] = (unsigned short)v;
+        if (!staged) refhi[row * 32 + lane] = (unsigned short)(v >> 16);
+    };
+    // sample index behind a reference (ties on distance go to the lower index)
+    auto gidx_of = [&](unsigned v) -> int {
+        v &= ~FLAG;
+        return staged ? __double2loint(st4[4 * v + 3]) : (int)v;
+    };
 
     for (int base = warp * 32; base < T.tnodes; base += NT) {
         const int t = base + lane;
@@ -911,10 +930,9 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                 zloc = __dadd_rn(P.zmn, __dmul_rn((double)iz, P.zsiz));
             }
         }
-        for (int l = 0; l < nlist; l++) {
-            tau[l * 32 + lane] = INF; // a list that is not full accepts anything in the radius
-            count[l * 32 + lane] = 0;
-        }
+        unsigned cnts = 0; // (cnt_reg) entries kept per octant
+        if (OCT && !cnt_reg)
+            for (int l = 0; l < 8; l++) count[l * 32 + lane] = 0;
         const double rho = sqrt(sqdist_exact(xloc - cx, yloc - cy, zloc - cz, rs));
         // candidates whose squared distance from the centre exceeds `limit` cannot be kept
         auto limit_of = [&](double tmax) {
@@ -925,16 +943,22 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         bool done = !active, changed = false;
         int tested = 0;
 
-        // the list of a candidate at squared distance h (octant l), sample index gf
-        // Octant search: puts a candidate (octant l, squared distance h, sample index gf) into
-        // its list, kept sorted by (distance, index): entries farther than the newcomer move up
-        // one place, the farthest falls off a full list.  The stream arrives roughly nearest
-        // first, so the newcomer usually lands at or next to the end.
+        // Octant search: eight lists of `cap` entries kept sorted by (distance, index); a full
+        // list's last entry is its bound, a list that is not full accepts anything in the
+        // radius.  Entries farther than a newcomer move up one place, the farthest falls off
+        // a full list; the stream arrives roughly nearest first, so the newcomer usually lands
+        // at or next to the end.
         // Without octants the one list of ndmax entries is kept UNSORTED in `ng` interleaved
         // groups (rows g, g + ng, ...) whose farthest entries are tracked (tau[g], count[g] =
         // its row); the farthest of all (gtau, vrow: registers) is what a newcomer replaces,
         // after which one group and the ng group maxima are looked at again: 4 + 8 loads
         // instead of 32.
+        auto oct_count = [&](int l) -> int {
+            return cnt_reg ? (int)((cnts >> (4 * l)) & 15u) : (int)count[l * 32 + lane];
+        };
+        auto oct_bound = [&](int l) -> double {
+            return oct_count(l) == cap ? keys[(l * cap + cap - 1) * 32 + lane] : INF;
+        };
         double gtau = INF; // (no octants) bound of the list: farthest kept once it is full
         int gn = 0, vrow = 0;
         const int ng = cap >= 32 ? 8 : cap >= 12 ? 4 : cap >= 6 ? 2 : 1;
@@ -944,7 +968,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
             for (int r = g + ng; r < cap; r += ng) {
                 const double k = keys[r * 32 + lane];
                 bool gt = k > bk;
-                if (k == bk) gt = ((unsigned)gidx[r * 32 + lane] & GM) > ((unsigned)gidx[bi * 32 + lane] & GM);
+                if (k == bk) gt = gidx_of(ref_get(r)) > gidx_of(ref_get(bi));
                 if (gt) { bk = k; bi = r; }
             }
             tau[g * 32 + lane] = bk;
@@ -957,72 +981,68 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                 const double k = tau[g * 32 + lane];
                 bool gt = k > bk;
                 if (k == bk)
-                    gt = ((unsigned)gidx[count[g * 32 + lane] * 32 + lane] & GM) >
-                         ((unsigned)gidx[count[bg * 32 + lane] * 32 + lane] & GM);
+                    gt = gidx_of(ref_get(count[g * 32 + lane])) > gidx_of(ref_get(count[bg * 32 + lane]));
                 if (gt) { bk = k; bg = g; }
             }
             gtau = bk;
             vrow = count[bg * 32 + lane];
             changed = true;
         };
-        auto keep = [&](int l, double h, unsigned gf) {
+        // a candidate: octant l, squared distance h, reference v (its sample index: g)
+        auto keep = [&](int l, double h, unsigned v, int g) {
             if constexpr (!OCT) {
                 if (h > gtau) return;
                 if (gn < cap) {
                     keys[gn * 32 + lane] = h;
-                    gidx[gn * 32 + lane] = (int)gf;
+                    ref_put(gn, v);
                     if (++gn < cap) return;
-                    for (int g = 0; g < ng; g++) farthest_of_group(g); // full: the bounds start
+                    for (int gr = 0; gr < ng; gr++) farthest_of_group(gr); // full: the bounds start
                 } else { // it must beat the farthest kept, (gtau, index) lexicographically
-                    if (h == gtau && (gf & GM) > ((unsigned)gidx[vrow * 32 + lane] & GM)) return;
+                    if (h == gtau && g > gidx_of(ref_get(vrow))) return;
                     keys[vrow * 32 + lane] = h;
-                    gidx[vrow * 32 + lane] = (int)gf;
+                    ref_put(vrow, v);
                     farthest_of_group(vrow % ng);
                 }
                 farthest_of_all();
                 return;
             }
-            const double tl = tau[l * 32 + lane];
-            if (h > tl) return;
-            int n = count[l * 32 + lane], e;
+            int n = oct_count(l), e;
             const int row0 = l * cap;
-            if (n == cap) { // full: it must beat the farthest kept, (tl, index) lexicographically
+            if (n == cap) { // full: it must beat the farthest kept, (bound, index) lexicographically
                 e = cap - 1;
-                if (h == tl && (gf & GM) > ((unsigned)gidx[(row0 + e) * 32 + lane] & GM)) return;
+                const double tl = keys[(row0 + e) * 32 + lane];
+                if (h > tl) return;
+                if (h == tl && g > gidx_of(ref_get(row0 + e))) return;
+                changed = true; // the bound of this list moves
             } else {
                 e = n++;
-                count[l * 32 + lane] = (unsigned short)n;
+                if (cnt_reg) cnts += 1u << (4 * l);
+                else count[l * 32 + lane] = (unsigned short)n;
+                if (n == cap) changed = true; // a full list bounds what can still be kept
             }
-            double last = h; // what ends up in the last place
-            bool first = true;
             while (e > 0) {
                 const double k = keys[(row0 + e - 1) * 32 + lane];
                 if (k < h) break;
-                const unsigned gk = (unsigned)gidx[(row0 + e - 1) * 32 + lane];
-                if (k == h && (gk & GM) < (gf & GM)) break;
+                const unsigned vk = ref_get(row0 + e - 1);
+                if (k == h && gidx_of(vk) < g) break;
                 keys[(row0 + e) * 32 + lane] = k;
-                gidx[(row0 + e) * 32 + lane] = (int)gk;
-                if (first) { last = k; first = false; }
+                ref_put(row0 + e, vk);
                 e--;
             }
             keys[(row0 + e) * 32 + lane] = h;
-            gidx[(row0 + e) * 32 + lane] = (int)gf;
-            if (n == cap) { // a full list bounds what can still be kept
-                tau[l * 32 + lane] = last;
-                changed = true;
-            }
+            ref_put(row0 + e, v);
         };
         // squared search distance of a sample from the node, its octant and whether it may be
         // used at all; point1 = node, point2 = sample (super_block.py:301-305)
-        auto measure = [&](double sx_, double sy_, double sz_, int g, double &h, int &l, unsigned &gf) {
+        auto measure = [&](double sx_, double sy_, double sz_, double &h, int &l, bool &self) {
             const double dx = __dsub_rn(xloc, sx_), dy = __dsub_rn(yloc, sy_), dz = __dsub_rn(zloc, sz_);
             h = sqdist_exact(dx, dy, dz, rs);
             l = OCT ? octant_of_neg(dx, dy, dz) : 0;
-            gf = (unsigned)g;
+            self = false;
             // super_block.py:306, and the list's bound as it stands (keep() looks again)
-            bool ok = !(h > P.radsqd) && !(h > (OCT ? tau[l * 32 + lane] : gtau));
+            bool ok = !(h > P.radsqd) && !(h > (OCT ? oct_bound(l) : gtau));
             if (PTS && excl && coincident(dx, dy, dz)) { // krige3d.py:359-363
-                if (OCT) gf |= ~GM;    // takes its place in the octant, dropped afterwards
+                if (OCT) self = true;  // takes its place in the octant, dropped afterwards
                 else ok = false;       // never a candidate
             }
             return ok;
@@ -1032,8 +1052,9 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
             for (int c0 = 0; c0 < nsorted; c0 += K3D_SCHUNK) {
                 if (!done) {
                     if (changed) { // a bound moved: what is the farthest anything can still be?
-                        double tmax = OCT ? tau[lane] : gtau;
-                        for (int l = 1; l < nlist; l++) tmax = fmax(tmax, tau[l * 32 + lane]);
+                        double tmax = OCT ? oct_bound(0) : gtau;
+                        if (OCT)
+                            for (int l = 1; l < 8; l++) tmax = fmax(tmax, oct_bound(l));
                         limit = limit_of(tmax);
                         changed = false;
                     }
@@ -1046,18 +1067,18 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                     const int c1 = min(c0 + K3D_SCHUNK, nsorted);
                     for (int c = c0; c < c1; c += 4) {
                         double h[4];
-                        int l[4];
-                        unsigned gf[4];
-                        bool ok[4];
+                        int l[4], g[4];
+                        bool ok[4], self[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const double2 *rec = reinterpret_cast<const double2 *>(st4 + 4 * (c + j));
                             const double2 a = rec[0], b = rec[1];
-                            ok[j] = measure(a.x, a.y, b.x, __double2loint(b.y), h[j], l[j], gf[j]);
+                            g[j] = __double2loint(b.y);
+                            ok[j] = measure(a.x, a.y, b.x, h[j], l[j], self[j]);
                         }
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            if (ok[j]) keep(l[j], h[j], gf[j]);
+                            if (ok[j]) keep(l[j], h[j], (unsigned)(c + j) | (self[j] ? FLAG : 0u), g[j]);
                     }
                     tested += c1 - c0;
                 }
@@ -1077,25 +1098,28 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                     for (int i = lo; i < hi; i++) {
                         double h;
                         int l;
-                        unsigned gf;
-                        if (measure(in.sx[i], in.sy[i], in.sz[i], i, h, l, gf)) keep(l, h, gf);
+                        bool self;
+                        if (measure(in.sx[i], in.sy[i], in.sz[i], h, l, self))
+                            keep(l, h, (unsigned)i | (self ? FLAG : 0u), i);
                     }
                 tested += hi - lo;
             }
         }
 
         // ---- 5. what the reference keeps (super_block.py:185-224, krige3d.py:356-375) -----
-        int tot = 0; // kept entries, compacted to rows 0.. of the lane's column
+        // The references become sample indices (32 bits, in the rows of `outl` once the keys
+        // are dead); kept entries are compacted to rows 0.. of the lane's column first.
+        int tot = 0;
         if (active) {
             if (OCT) {
                 for (int l = 0; l < 8; l++) {
-                    const int n = count[l * 32 + lane];
+                    const int n = oct_count(l);
                     for (int k = 0; k < n; k++) {
                         const int row = l * cap + k;
-                        const int gf = gidx[row * 32 + lane];
-                        if (gf < 0) continue; // the sample at the location itself
+                        const unsigned v = ref_get(row);
+                        if (v & FLAG) continue; // the sample at the location itself
                         if (tot != row) {
-                            gidx[tot * 32 + lane] = gf;
+                            ref_put(tot, v);
                             keys[tot * 32 + lane] = keys[row * 32 + lane];
                         }
                         tot++;
@@ -1114,20 +1138,27 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                 for (int e = j + 1; e < tot; e++) {
                     const double k = keys[e * 32 + lane];
                     bool lt = k < bk;
-                    if (k == bk) lt = gidx[e * 32 + lane] < gidx[bi * 32 + lane];
+                    if (k == bk) lt = gidx_of(ref_get(e)) < gidx_of(ref_get(bi));
                     if (lt) { bk = k; bi = e; }
                 }
                 if (bi != j) {
-                    const int gj = gidx[j * 32 + lane], gb = gidx[bi * 32 + lane];
+                    const unsigned vj = ref_get(j), vb = ref_get(bi);
                     keys[bi * 32 + lane] = keys[j * 32 + lane];
-                    gidx[bi * 32 + lane] = gj;
+                    ref_put(bi, vj);
                     keys[j * 32 + lane] = bk;
-                    gidx[j * 32 + lane] = gb;
+                    ref_put(j, vb);
                 }
             }
         }
+        int gout[2] = {0, 0}; // (rows are handed over through registers two at a time: the
+                              //  staging overlays the keys of every lane of the warp)
         __syncwarp(); // the keys are dead: the output staging overlays them
-        for (int e = 0; e < na; e++) outl[e * 33 + lane] = (unsigned)gidx[e * 32 + lane];
+        for (int e0 = 0; e0 < na; e0 += 2) {
+            gout[0] = gidx_of(ref_get(e0));
+            if (e0 + 1 < na) gout[1] = gidx_of(ref_get(e0 + 1));
+            outl[e0 * 33 + lane] = (unsigned)gout[0];
+            if (e0 + 1 < na) outl[(e0 + 1) * 33 + lane] = (unsigned)gout[1];
+        }
         __syncwarp();
         const int nact = min(32, T.tnodes - base);
         const int pieces = P.ndmax >> 2; // 16-byte pieces of a node's row
@@ -1786,10 +1817,12 @@ int make_scfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_
     double best = -1.0;
     SCfg pick = *c;
     for (int pass = 0; pass < 2 && best < 0.0; pass++) {
-        c->cst = pass == 0 ? want : floor_cst;
         for (int warps = 1; warps <= 8; warps++) {
             if (force_warps ? warps != force_warps : warps > wneed) continue;
             c->warps = warps;
+            c->cst = pass == 0 ? want : floor_cst;
+            // (room for the upper halves of the references of a tile that is not staged)
+            if (c->cst + 4 < 2 * warps * c->nlist * c->cap) c->cst = roundup32(2 * warps * c->nlist * c->cap);
             // the unsorted candidate list overlays the selection lists: 7 bytes each
             c->cs = roundup32((int)(2.5 * mean_cand) + 64);
             if (c->cs < warps * c->pw_bytes / 7) c->cs = (warps * c->pw_bytes / 7) & ~31;
@@ -1799,7 +1832,7 @@ int make_scfg(const K3dParams *p, double mean_cand, double tile_nodes, int smem_
             if (bytes + 256 > smem_max) continue;
             int ctas = (smem_max + 1024) / (bytes + 256 + 1024);
             if (ctas > 32) ctas = 32;
-            if (ctas * warps > 16) ctas = 16 / warps > 0 ? 16 / warps : 1; // ~120 registers per thread
+            if (ctas * warps > 16) ctas = 16 / warps > 0 ? 16 / warps : 1; // ~125 registers per thread
             // resident warps, discounted by the share of a tile's warp slots that idle
             const double wp = ceil(tile_nodes / 32.0), passes = ceil(wp / warps);
             const double score = ctas * warps * ((tile_nodes / 32.0) / (passes * warps)) + 1e-3 * warps;
