@@ -32,6 +32,14 @@ def build(force=False, verbose=False, out=None, defines=()):
     return out
 
 
+DEBUG_OUT = os.path.join(HERE, "libk3d_debug.so")
+
+
+def build_debug(force=False):
+    """The bounds-checking variant (-DK3D_DEBUG) the debug-build test runs the parity cases on."""
+    return build(force=force, out=DEBUG_OUT, defines=("K3D_DEBUG",))
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,

@@ -58,6 +58,23 @@
 // measured as the difference between 2.5 and 0.2 "no instruction" stall cycles per issue.
 #define K3D_PHASE_BARRIER() __syncthreads()
 
+// -DK3D_DEBUG: every index into the shared-memory carve-up that is computed from data (list
+// rows, stage places, round-table slots, matrix positions) is checked, and a violation traps
+// the kernel with a message.  compute-sanitizer is not available on the pool; the parity suite
+// is run against this build instead (tests/test_gpu_debug_build.py).
+#ifdef K3D_DEBUG
+#define K3D_CHECK(cond, what, a, b)                                                        \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            printf("k3d debug: %s (%d, %d) block %d thread %d line %d\n", what, (int)(a), \
+                   (int)(b), (int)blockIdx.x, (int)threadIdx.x, __LINE__);                 \
+            __trap();                                                                      \
+        }                                                                                  \
+    } while (0)
+#else
+#define K3D_CHECK(cond, what, a, b) do { } while (0)
+#endif
+
 #ifdef K3D_PHASE_CLOCKS /* diagnostic build: cycles a warp spends in each phase of the solve kernel */
 __device__ unsigned long long g_phase_clk[8];
 #define K3D_CLK(i) do { const long long c_ = clock64(); if (lane == 0) pc_[i] += c_ - pt_; pt_ = c_; } while (0)
@@ -746,7 +763,10 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
             nr = nr < NT ? nr : NT;
             for (int q = warp; q < nr; q += cfg.warps) {
                 const int qlo = chunk[q], qcnt = chunk[NT + q], qoff = chunk[2 * NT + q];
-                for (int i = lane; i < qcnt; i += 32) gtmp[qoff + i] = qlo + i;
+                for (int i = lane; i < qcnt; i += 32) {
+                    K3D_CHECK(qoff + i >= 0 && qoff + i < cfg.cs, "candidate list index", qoff + i, cfg.cs);
+                    gtmp[qoff + i] = qlo + i;
+                }
             }
         }
         __syncthreads();
@@ -862,6 +882,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
                 const int bin = btmp[i];
                 if (bin != 255) {
                     const int pos = bstart[bin] + whist[warp * K3D_SBINS + bin] + rtmp[i];
+                    K3D_CHECK(pos >= 0 && pos < cfg.cst, "stage place", pos, cfg.cst);
                     const int g = gtmp[i];
                     double2 *rec = reinterpret_cast<double2 *>(st4 + 4 * pos);
                     rec[0] = make_double2(in.sx[g], in.sy[g]);
@@ -901,6 +922,8 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         return v;
     };
     auto ref_put = [&](int row, unsigned v) {
+        K3D_CHECK(row >= 0 && row < E, "list row", row, E);
+        K3D_CHECK(!staged || (v & 0x7fffu) < (unsigned)nsorted, "stage reference", v, nsorted);
         ref[row * 32 + lane] = (unsigned short)v;
         if (!staged) refhi[row * 32 + lane] = (unsigned short)(v >> 16);
     };
@@ -1156,6 +1179,7 @@ k3d_search_kernel(const __grid_constant__ K3dParams P, const K3dInputs in, const
         for (int e0 = 0; e0 < na; e0 += 2) {
             gout[0] = gidx_of(ref_get(e0));
             if (e0 + 1 < na) gout[1] = gidx_of(ref_get(e0 + 1));
+            K3D_CHECK(((e0 + 1) * 33 + lane) * 4 < E * 256, "output staging", e0, E);
             outl[e0 * 33 + lane] = (unsigned)gout[0];
             if (e0 + 1 < na) outl[(e0 + 1) * 33 + lane] = (unsigned)gout[1];
         }
@@ -1355,6 +1379,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         unsigned freem = ~used & (na == 32 ? 0xffffffffu : ((1u << na) - 1u));
                         const int r = __popc(unm & ltm);
                         for (int k = 0; k < r; k++) freem &= freem - 1u;
+                        K3D_CHECK(r < ndp && freem != 0u, "free position", r, na);
                         newpos[r] = (unsigned char)(__ffs(freem) - 1);
                         newid[r] = myid;
                     }
@@ -1369,6 +1394,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             __syncwarp();
             for (int k = lane; k < nnew; k += 32) {
                 const int pos = newpos[k], g = newid[k];
+                K3D_CHECK(pos >= 0 && pos < na && g >= 0 && g < (int)in.nd, "newcomer position / sample", pos, g);
                 pid[pos] = g;
                 const double x = in.sx[g], y = in.sy[g], z = in.sz[g];
                 if (cfg.need_xyz) { px[pos] = x; py[pos] = y; pz[pos] = z; }
@@ -1413,6 +1439,8 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     base = atomicAdd(&s_nrounds[tt & 1], nr);
                 }
                 base = __shfl_sync(FULL, base, 0);
+                K3D_CHECK(base + nr <= cfg.warps * b_rounds_per_warp(cfg), "round table", base + nr,
+                          cfg.warps * b_rounds_per_warp(cfg));
                 for (int r = lane; r < nr; r += 32) s_rtab[base + r] = (unsigned short)((warp << 8) | r);
             }
         }
@@ -1503,10 +1531,15 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     }
                     acc += c;
                 }
-                if (BLOCK && rhs) // partial sum of the block average, added up by the owner
+                K3D_CHECK(jw >= 0 && jw < cfg.warps && p1 >= 0 && p1 < ndp, "round owner / position", jw, p1);
+                if (BLOCK && rhs) { // partial sum of the block average, added up by the owner
+                    K3D_CHECK(prt * napad_max + p1 < nsplit * napad_max, "partial sum slot", prt, p1);
                     sts_f64(jb + o_part + ((prt * napad_max + p1) << 3), acc);
-                else
+                } else {
+                    K3D_CHECK(pk(jR - p1, rhs ? 1 : jR - p2r) < cfg.ntri && jR - p1 >= (rhs ? 1 : jR - p2r),
+                              "packed matrix entry", jR - p1, rhs ? 1 : jR - p2r);
                     sts_f64(jb + (pk(jR - p1, rhs ? 1 : jR - p2r) << 3), acc);
+                }
             }
         }
         K3D_CLK(2); // covariance rounds
