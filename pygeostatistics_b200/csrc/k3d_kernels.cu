@@ -155,6 +155,8 @@ struct KPrep {
     double cc[K3D_MAXNST];
     double aa[K3D_MAXNST];
     double eps0s;   // K3D_EPS / a0^2: the "zero distance" test in scaled units
+    double epsblk;  // block kriging: a sample and a block point whose structure-0 distance
+                    // h2 is at least this are more than sqrt(K3D_EPS) apart (4 EPS |rs0|_F^2)
     int it[K3D_MAXNST];
 };
 
@@ -1508,7 +1510,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 double acc = 0.0;
 #pragma unroll 1
                 for (int k = 0; k < nsub; k++, a2 += ustride << 3) {
-                    double c = 0.0;
+                    double c = 0.0, h20 = 0.0;
                     bool zero = false;
                     uint32_t b1 = a1, b2 = a2;
 #pragma unroll 1
@@ -1517,12 +1519,14 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         const double uz = lds_f64(b1 + 16), vz = lds_f64(b2 + 16);
                         const double dx = u.x - v.x, dy = u.y - v.y, dz = uz - vz;
                         const double h2 = dx * dx + dy * dy + dz * dz;
-                        if (st == 0) zero = h2 < Q.eps0s;
+                        if (st == 0) { zero = h2 < Q.eps0s; h20 = h2; }
                         c += cova_term(P, Q, st, h2, s_exptab);
                     }
                     if (zero) c = P.maxcov; // krige3d.py:853-855
                     if constexpr (BLOCK) {
-                        if (rhs) { // krige3d.py:792-796: a block point on the sample loses the nugget
+                        // krige3d.py:792-796: a block point on the sample loses the nugget (only
+                        // looked at when the structure-0 distance does not rule it out)
+                        if (rhs && h20 < Q.epsblk) {
                             const int sub = p2r - ndp + k;
                             const double dx = relx - db[sub], dy = rely - db[P.ndb + sub],
                                          dz = relz - db[2 * P.ndb + sub];
@@ -1820,6 +1824,9 @@ void make_prep(const K3dParams *p, KPrep *q)
     }
     const double a0 = p->it[0] == 4 ? 1.0 : p->aa[0];
     q->eps0s = K3D_EPS / (a0 * a0);
+    double fro = 0.0; // h2 = |rs0 d|^2 <= |rs0|_F^2 |d|^2
+    for (int k = 0; k < 9; k++) fro += q->rs[0][k] * q->rs[0][k];
+    q->epsblk = 4.0 * K3D_EPS * fro;
 }
 
 // ---- search kernel plan: warps per CTA and stage capacity ---------------------------------
