@@ -354,6 +354,32 @@ __device__ __forceinline__ double cova_term(const K3dParams &P, const KPrep &Q, 
     return c * cos(sqrt(h2) * 3.141592653589793);
 }
 
+// The same term at four distances at once (the block points of one right-hand-side item):
+// one dispatch on the model for the four, whose evaluations are independent work.
+__device__ __forceinline__ void cova_term4(const K3dParams &P, const KPrep &Q, int s,
+                                           const double (&h2)[4], double (&acc)[4],
+                                           const double *__restrict__ exptab)
+{
+    const double c = Q.cc[s];
+    const int it = Q.it[s];
+    if (it == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double hr = sqrt_pos(h2[j]);
+            const double v = c * (1.0 - hr * (1.5 - 0.5 * h2[j]));
+            acc[j] += h2[j] < 1.0 ? v : 0.0;
+        }
+    } else if (it == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[j] += c * exp_neg(-3.0 * sqrt_pos(h2[j]), exptab);
+    } else if (it == 3) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[j] += c * exp_neg(-3.0 * h2[j], exptab);
+    } else {
+        for (int j = 0; j < 4; j++) acc[j] += cova_term(P, Q, s, h2[j], exptab);
+    }
+}
+
 // u = rs[s] * (x,y,z) for every structure, written as record idx (4 doubles per structure:
 // x, y, z, pad; records `stride` doubles apart)
 __device__ __forceinline__ void transform_point(const K3dParams &P, const KPrep &Q, double x,
@@ -1508,9 +1534,56 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                     }
                 }
                 double acc = 0.0;
+                bool done_block = false;
+                if constexpr (BLOCK) {
+                    if (rhs) { // a sample against its part of the block points, four at a time:
+                               // one model dispatch and one load of the sample's record per four
+                        done_block = true;
 #pragma unroll 1
-                for (int k = 0; k < nsub; k++, a2 += ustride << 3) {
-                    double c = 0.0, h20 = 0.0;
+                        for (int k0 = 0; k0 < nsub; k0 += 4, a2 += 4 * (ustride << 3)) {
+                            const int kn = nsub - k0 < 4 ? nsub - k0 : 4;
+                            double c4[4] = {0.0, 0.0, 0.0, 0.0}, h20[4] = {1.0, 1.0, 1.0, 1.0};
+                            uint32_t b1 = a1, b2 = a2;
+#pragma unroll 1
+                            for (int st = 0; st < P.nst; st++, b1 += 32, b2 += 32) {
+                                const double2 u = lds_f64x2(b1);
+                                const double uz = lds_f64(b1 + 16);
+                                double h2[4];
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    // (points past the part repeat its last one; not added up)
+                                    const uint32_t bj = b2 + (j < kn ? j : kn - 1) * (ustride << 3);
+                                    const double2 v = lds_f64x2(bj);
+                                    const double vz = lds_f64(bj + 16);
+                                    const double dx = u.x - v.x, dy = u.y - v.y, dz = uz - vz;
+                                    h2[j] = dx * dx + dy * dy + dz * dz;
+                                }
+                                if (st == 0) {
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) h20[j] = h2[j];
+                                }
+                                cova_term4(P, Q, st, h2, c4, s_exptab);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                if (j < kn) {
+                                    double c = h20[j] < Q.eps0s ? P.maxcov : c4[j]; // krige3d.py:853-855
+                                    // krige3d.py:792-796: a block point on the sample loses the nugget
+                                    // (only looked at when the structure-0 distance does not rule it out)
+                                    if (h20[j] < Q.epsblk) {
+                                        const int sub = p2r - ndp + k0 + j;
+                                        const double dx = relx - db[sub], dy = rely - db[P.ndb + sub],
+                                                     dz = relz - db[2 * P.ndb + sub];
+                                        if (dx * dx + dy * dy + dz * dz < K3D_EPS) c -= P.c0;
+                                    }
+                                    acc += c;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (!done_block) {
+                    double c = 0.0;
                     bool zero = false;
                     uint32_t b1 = a1, b2 = a2;
 #pragma unroll 1
@@ -1519,21 +1592,11 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         const double uz = lds_f64(b1 + 16), vz = lds_f64(b2 + 16);
                         const double dx = u.x - v.x, dy = u.y - v.y, dz = uz - vz;
                         const double h2 = dx * dx + dy * dy + dz * dz;
-                        if (st == 0) { zero = h2 < Q.eps0s; h20 = h2; }
+                        if (st == 0) zero = h2 < Q.eps0s;
                         c += cova_term(P, Q, st, h2, s_exptab);
                     }
                     if (zero) c = P.maxcov; // krige3d.py:853-855
-                    if constexpr (BLOCK) {
-                        // krige3d.py:792-796: a block point on the sample loses the nugget (only
-                        // looked at when the structure-0 distance does not rule it out)
-                        if (rhs && h20 < Q.epsblk) {
-                            const int sub = p2r - ndp + k;
-                            const double dx = relx - db[sub], dy = rely - db[P.ndb + sub],
-                                         dz = relz - db[2 * P.ndb + sub];
-                            if (dx * dx + dy * dy + dz * dz < K3D_EPS) c -= P.c0;
-                        }
-                    }
-                    acc += c;
+                    acc = c;
                 }
                 K3D_CHECK(jw >= 0 && jw < cfg.warps && p1 >= 0 && p1 < ndp, "round owner / position", jw, p1);
                 if (BLOCK && rhs) { // partial sum of the block average, added up by the owner
