@@ -1968,7 +1968,9 @@ int make_bcfg(const K3dParams *p, double tile_nodes, int smem_max, int static_sm
     c->napad = (p->ndmax + 31) & ~31;
     c->nsplit = 1;
     if (p->ndb > 1) { // right-hand side work items of <= 4 block points, at most 8 per sample
-        c->nsplit = (p->ndb + 3) >> 2;
+        int ppi = 4; // tuning knob: K3D_BLOCK_PTS = block points per work item
+        if (const char *e = getenv("K3D_BLOCK_PTS")) ppi = atoi(e) > 0 ? atoi(e) : 4;
+        c->nsplit = (p->ndb + ppi - 1) / ppi;
         if (c->nsplit > 8) c->nsplit = 8;
     }
     // The kernel is latency bound, so more warps per SM help, but every warp starts its walk

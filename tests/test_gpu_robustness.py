@@ -315,3 +315,35 @@ def test_automatic_bricks_for_small_super_blocks():
     k3 = Krige3d(par3, data=data3)
     k3.prepare()
     assert k3._brick() == (1, 1, 1)
+
+
+def test_repeated_runs_on_one_object_and_cached_setup():
+    """A second kt3d() on the same object must report the same original row numbers (the
+    set-up always starts from the records in file order), a second object on the same data
+    re-uses the cached set-up, and an edit of the data is seen."""
+    from pygeostatistics_b200 import Krige3d
+    from pygeostatistics_b200 import krige3d as K
+    par, data, sec = k3d_configs.config("c3", 0.15)
+    K.clear_setup_cache()
+    k = Krige3d(par, data=data)
+    k.verbose = False
+    k.kt3d(neighbours=True)
+    nb1, e1 = k.neighbours.copy(), k.estimation.copy()
+    s1 = k.searcher
+    k.kt3d(neighbours=True)
+    assert np.array_equal(k.neighbours, nb1) and np.array_equal(k.estimation, e1, equal_nan=True)
+    assert k.searcher is s1 and len(K._SEARCHERS) == 1
+    k2 = Krige3d(par, data={n: v.copy() for n, v in data.items()})
+    k2.verbose = False
+    k2.kt3d(neighbours=True)
+    assert k2.searcher is s1                      # same bytes: same set-up
+    assert np.array_equal(k2.neighbours, nb1)
+    d3 = {n: v.copy() for n, v in data.items()}
+    d3['v'][5] += 1.0
+    k3 = Krige3d(par, data=d3)
+    k3.verbose = False
+    k3.kt3d()
+    assert k3.searcher is not s1 and len(K._SEARCHERS) == 2
+    assert not np.array_equal(k3.estimation, e1, equal_nan=True)
+    st, ores = oracle_run(par, d3, sec)
+    compare(k3, st, ores, vmax=float(np.max(np.abs(d3['v']))), check_neighbours=False)
