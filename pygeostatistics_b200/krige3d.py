@@ -35,6 +35,19 @@ from .super_block import SuperBlockSearcher, brick_template
 EPS = np.finfo(float).eps
 
 _PINNED = []  # [pinned tensor, weakref to the ndarray it was lent to (or None)]
+_PINNED_MAX = 8  # buffers kept (est, var, status and the three neighbour arrays of one run, + slack)
+
+
+def release_host_buffers():
+    """Drop the pooled page-locked result buffers that are not lent out, the shared result
+    buffers of multi-rank runs nobody holds any more, the cached set-ups, and what the native
+    library keeps between calls (k3d_release: scratch pool, timing events)."""
+    _PINNED[:] = [e for e in _PINNED if not (e[1] is None or e[1]() is None)]
+    for key in [k for k, sg in _SHARED.items() if sg.free()]:
+        _SHARED.pop(key).close()
+    clear_setup_cache()
+    _native.check(_native.lib().k3d_release())
+
 
 
 def _pinned_array(numel, dtype):
@@ -50,9 +63,9 @@ def _pinned_array(numel, dtype):
     if entry is None:
         entry = [torch.empty(max(numel, 1), dtype=dtype, pin_memory=True), None]
         _PINNED.append(entry)
-        if len(_PINNED) > 16:  # drop idle buffers, oldest first
+        if len(_PINNED) > _PINNED_MAX:  # drop idle buffers, oldest first
             idle = [id(e) for e in _PINNED[:-1] if e[1] is None or e[1]() is None]
-            drop = set(idle[:len(_PINNED) - 16])
+            drop = set(idle[:len(_PINNED) - _PINNED_MAX])
             _PINNED[:] = [e for e in _PINNED if id(e) not in drop]  # (list.remove would compare tensors)
     view = entry[0][:numel]
     arr = view.numpy()

@@ -347,3 +347,12 @@ def test_repeated_runs_on_one_object_and_cached_setup():
     assert not np.array_equal(k3.estimation, e1, equal_nan=True)
     st, ores = oracle_run(par, d3, sec)
     compare(k3, st, ores, vmax=float(np.max(np.abs(d3['v']))), check_neighbours=False)
+    # everything the package and the library keep between runs can be given back
+    import pygeostatistics_b200 as pkg
+    del k, k2, k3, nb1, e1
+    pkg.release_host_buffers()
+    assert len(K._SEARCHERS) == 0 and all(e[1] is not None and e[1]() is not None for e in K._PINNED)
+    k4 = Krige3d(par, data=data)
+    k4.verbose = False
+    k4.kt3d()
+    assert np.isfinite(k4.estimation).any()
