@@ -26,6 +26,7 @@ SELECTED = [
     "tests/test_gpu_robustness.py::test_bricks_of_super_blocks",
     "tests/test_gpu_robustness.py::test_largest_supported_system",
     "tests/test_gpu_robustness.py::test_duplicate_samples_are_singular",
+    "tests/test_gpu_robustness.py::test_random_parameter_sets_against_oracle",
 ]
 
 
