@@ -354,29 +354,31 @@ __device__ __forceinline__ double cova_term(const K3dParams &P, const KPrep &Q, 
     return c * cos(sqrt(h2) * 3.141592653589793);
 }
 
-// The same term at four distances at once (the block points of one right-hand-side item):
-// one dispatch on the model for the four, whose evaluations are independent work.
-__device__ __forceinline__ void cova_term4(const K3dParams &P, const KPrep &Q, int s,
-                                           const double (&h2)[4], double (&acc)[4],
+// The same term at N distances at once (the block points of one right-hand-side item; the
+// two records a round pairs with a position): one dispatch on the model for the N, whose
+// evaluations are independent work.
+template <int N>
+__device__ __forceinline__ void cova_termN(const K3dParams &P, const KPrep &Q, int s,
+                                           const double (&h2)[N], double (&acc)[N],
                                            const double *__restrict__ exptab)
 {
     const double c = Q.cc[s];
     const int it = Q.it[s];
     if (it == 1) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < N; j++) {
             const double hr = sqrt_pos(h2[j]);
             const double v = c * (1.0 - hr * (1.5 - 0.5 * h2[j]));
             acc[j] += h2[j] < 1.0 ? v : 0.0;
         }
     } else if (it == 2) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[j] += c * exp_neg(-3.0 * sqrt_pos(h2[j]), exptab);
+        for (int j = 0; j < N; j++) acc[j] += c * exp_neg(-3.0 * sqrt_pos(h2[j]), exptab);
     } else if (it == 3) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[j] += c * exp_neg(-3.0 * h2[j], exptab);
+        for (int j = 0; j < N; j++) acc[j] += c * exp_neg(-3.0 * h2[j], exptab);
     } else {
-        for (int j = 0; j < 4; j++) acc[j] += cova_term(P, Q, s, h2[j], exptab);
+        for (int j = 0; j < N; j++) acc[j] += cova_term(P, Q, s, h2[j], exptab);
     }
 }
 
@@ -1267,6 +1269,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = cfg.warps * 32;
     const int ndp = cfg.ndp;
+    constexpr bool PAIRED = AMAX == 11 || BLOCK; // covariance rounds pair two new records (see below)
 
     uint16_t *tri = (uint16_t *)smem;
     double *udb = (double *)(smem + b_off_udb(cfg)); // [3*nst][ndb] block points, structure space
@@ -1451,16 +1454,25 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
             __syncwarp();
 
             // publish this warp's covariance job for the pooled phase: one job word and one
-            // round-table entry per round of 32 work items.  Pair rounds: one per newcomer
-            // (lane = the other position), or the whole triangle 32 pairs at a time; then the
-            // right-hand side: lane = sample, one round per part of the block discretisation
+            // round-table entry per round of 32 work items (lane = a position of the system).
+            // Partial update: one round per newcomer, then the right-hand side (lane = sample);
+            // or (PAIRED: the instantiations with registers to spare -- the 44-row solver at
+            // 128 registers, block kriging -- where it measured 3 % faster; on the 36-row
+            // solver at 96 registers it spills and measured 3 % slower) the records that are
+            // new to the system -- the newcomers and, for point kriging, the node itself --
+            // go TWO per round: a lane evaluates both against its position with one load of
+            // the position's record and one dispatch on the model.  Full rebuild: the whole triangle 32 pairs
+            // at a time, then the right-hand side (lane = sample).  Block kriging: one
+            // right-hand-side round per part of the block discretisation.
             {
-                const int npairs = full ? (na * (na - 1)) >> 1 : nnew * na;
-                const int npr = full ? (npairs + 31) >> 5 : nnew;
-                const int nr = npr + nsplit * ((na + 31) >> 5);
+                const bool dbl = PAIRED && !full;
+                const int nrec = nnew + (BLOCK ? 0 : 1);
+                const int npr = full ? (((na * (na - 1)) >> 1) + 31) >> 5 : dbl ? (nrec + 1) >> 1 : nnew;
+                const int nr = npr + ((dbl && !BLOCK) ? 0 : nsplit * ((na + 31) >> 5));
                 int base = 0;
                 if (lane == 0) {
-                    s_job[warp] = R | (na << 8) | (npr << 16) | (full ? 1 << 24 : 0);
+                    s_job[warp] = R | (na << 8) | (npr << 16) | (full ? 1 << 24 : 0) | (dbl ? 1 << 25 : 0) |
+                                  ((dbl ? nnew : 0) << 26);
                     if constexpr (BLOCK) {
                         s_jloc[warp][0] = xloc; s_jloc[warp][1] = yloc; s_jloc[warp][2] = zloc;
                     }
@@ -1494,6 +1506,47 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                 const uint32_t jb = a_w0 + jw * pwb;
                 const int job = lds_s32(a_job + 4 * jw);
                 const int jR = job & 255, jna = (job >> 8) & 255, npr = (job >> 16) & 255;
+                if (PAIRED && r < npr && ((job >> 25) & 1)) {
+                    // two records (newcomers, then the node) against the lane's position
+                    const int jnew = (job >> 26) & 63, nrec = jnew + (BLOCK ? 0 : 1);
+                    const int k0 = 2 * r, k1 = k0 + 1 < nrec ? k0 + 1 : k0;
+                    int pn0 = ndp, pn1 = ndp; // (the node's record follows the neighbours')
+                    if (k0 < jnew) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pn0) : "r"(jb + o_newpos + k0));
+                    if (k1 < jnew) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pn1) : "r"(jb + o_newpos + k1));
+                    const int q = min(lane, jna - 1); // idle lanes repeat the last position
+                    K3D_CHECK(pn0 <= ndp && pn1 <= ndp && q >= 0, "paired records", pn0, pn1);
+                    const uint32_t aq = jb + o_ut + q * (ustride << 3), ar0 = jb + o_ut + pn0 * (ustride << 3),
+                                   ar1 = jb + o_ut + pn1 * (ustride << 3);
+                    double c2[2] = {0.0, 0.0}, h20[2] = {1.0, 1.0};
+#pragma unroll 1
+                    for (int st = 0; st < P.nst; st++) {
+                        const double2 v = lds_f64x2(aq + 32 * st), u0 = lds_f64x2(ar0 + 32 * st),
+                                      u1 = lds_f64x2(ar1 + 32 * st);
+                        const double vz = lds_f64(aq + 32 * st + 16), u0z = lds_f64(ar0 + 32 * st + 16),
+                                     u1z = lds_f64(ar1 + 32 * st + 16);
+                        double h2[2];
+                        {
+                            const double dx = u0.x - v.x, dy = u0.y - v.y, dz = u0z - vz;
+                            h2[0] = dx * dx + dy * dy + dz * dz;
+                        }
+                        {
+                            const double dx = u1.x - v.x, dy = u1.y - v.y, dz = u1z - vz;
+                            h2[1] = dx * dx + dy * dy + dz * dz;
+                        }
+                        if (st == 0) { h20[0] = h2[0]; h20[1] = h2[1]; }
+                        cova_termN<2>(P, Q, st, h2, c2, s_exptab);
+                    }
+                    // krige3d.py:853-855; a newcomer pairs into the triangle, the node into the b row
+                    const int e0 = pn0 == ndp ? pk(jR - q, 1) : pk(jR - min(pn0, q), jR - max(pn0, q));
+                    K3D_CHECK(e0 >= 0 && e0 < cfg.ntri, "packed matrix entry", e0, cfg.ntri);
+                    sts_f64(jb + (e0 << 3), h20[0] < Q.eps0s ? P.maxcov : c2[0]);
+                    if (k1 != k0) {
+                        const int e1 = pn1 == ndp ? pk(jR - q, 1) : pk(jR - min(pn1, q), jR - max(pn1, q));
+                        K3D_CHECK(e1 >= 0 && e1 < cfg.ntri, "packed matrix entry", e1, cfg.ntri);
+                        sts_f64(jb + (e1 << 3), h20[1] < Q.eps0s ? P.maxcov : c2[1]);
+                    }
+                    continue;
+                }
                 // idle lanes repeat the last item of their kind (same value, same place)
                 const bool rhs = r >= npr;
                 int p1, p2r, prt = 0, nsub = 1;
@@ -1510,12 +1563,12 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
                         p2r = ndp;
                     }
                     p1 = min((rr << 5) + lane, jna - 1);
-                } else if (job >> 24) {
+                } else if (job >> 24 & 1) { // full rebuild: the triangle, 32 pairs at a time
                     const int w = min((r << 5) + lane, ((jna * (jna - 1)) >> 1) - 1);
                     const int rc = lds_u16(a_tri + 2 * w);
                     p1 = rc & 255;
                     p2r = (rc >> 8) + 1;
-                } else {
+                } else { // newcomer r against the lane's position
                     int pn;
                     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pn) : "r"(jb + o_newpos + r));
                     const int q = min(lane, jna - 1);
@@ -1562,7 +1615,7 @@ k3d_solve_kernel(const __grid_constant__ K3dParams P, const __grid_constant__ KP
 #pragma unroll
                                     for (int j = 0; j < 4; j++) h20[j] = h2[j];
                                 }
-                                cova_term4(P, Q, st, h2, c4, s_exptab);
+                                cova_termN<4>(P, Q, st, h2, c4, s_exptab);
                             }
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
