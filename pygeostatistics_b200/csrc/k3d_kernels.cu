@@ -6,27 +6,29 @@
 //   k3d_solve_kernel    kriging system assembly          krige3d.py:470-583, 748-801, 838-875
 //                       solve + estimate + variance      krige3d.py:590-614
 // The neighbour lists travel between them through global memory (HBM is not the bound:
-// 128 B per node against 6.5 TB/s), which lets the light search run at 32 warps per SM
-// and the register-heavy solve at up to 20.  The same kernels estimate at listed locations
-// (cross-validation / jackknife, krige3d.py:310-332, 359-363) when given a K3dPoints.
+// 128 B per node against 6.5 TB/s), which lets each kernel have its own shape: the search
+// is bounded by shared memory (12 warps per SM on config 3), the register-heavy solve runs
+// 16-20.  The same kernels estimate at listed locations (cross-validation / jackknife,
+// krige3d.py:310-332, 359-363) when given a K3dPoints.
 //
 // Mapping to the machine (DESIGN.md has the full account):
-//   * one CTA per "tile" = the grid nodes that fall in one super block; all of them
-//     search the same super blocks, so the candidate samples are staged ONCE per CTA
-//     into shared memory as SoA tiles, in ascending sorted-sample order;
-//   * one warp per node, each warp walking a boustrophedon path so that consecutive nodes
-//     are neighbours: lanes scan the candidates with the reference's exact (FMA-free)
-//     anisotropic distance under exact bounds inherited from the previous node, compact
-//     the hits with ballots and remove the surplus (octant rule, ndmax) by warp-wide
-//     lexicographic maxima;
-//   * the covariances the nodes in flight need are dealt out over the warps of the CTA in
-//     rounds of 32, evaluated from per-structure pre-scaled coordinates (no division);
+//   * one CTA per "tile" = the grid nodes that fall in one super block (or in a brick of
+//     super blocks when those hold few nodes); all of them search the same super blocks;
+//   * search: the tile's candidate samples are listed once per CTA, ordered by their
+//     distance from the centre of the tile (counting sort) and staged in shared memory;
+//     ONE THREAD PER NODE then streams them nearest-first -- all lanes of a warp read the
+//     same candidate -- evaluates the reference's exact (FMA-free) anisotropic distance,
+//     keeps the nearest per octant (or the ndmax nearest) in small shared-memory lists and
+//     stops as soon as the triangle inequality rules out what is left;
+//   * solve: one warp per node, each warp walking a boustrophedon path so that consecutive
+//     nodes are neighbours and the sample-sample covariances of the previous node are
+//     re-used; the covariances the nodes in flight need are dealt out over the warps of the
+//     CTA in rounds of 32, evaluated from per-structure pre-scaled coordinates (no division);
 //   * the (n+mdt) system is assembled in shared memory in a mirrored packed-triangular
-//     layout -- re-using the sample-sample covariances of the previous node -- bordered by
-//     the right-hand side and the data vector, so that a single register-resident LDL^T
-//     sweep (no pivoting: covariance block is SPD, the constraint Schur complement is
-//     definite) leaves the kriging variance and the estimate in the two border entries:
-//     no triangular solves, no weights materialised.
+//     layout, bordered by the right-hand side and the data vector, so that a single
+//     register-resident LDL^T sweep (no pivoting: covariance block is SPD, the constraint
+//     Schur complement is definite) leaves the kriging variance and the estimate in the two
+//     border entries: no triangular solves, no weights materialised.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see build.py).
 #include <cuda_runtime.h>
@@ -39,7 +41,7 @@
 
 #include "k3d.h"
 
-#define K3D_VERSION_STR "pygeostatistics_b200 k3d 0.1 (sm_100a)"
+#define K3D_VERSION_STR "pygeostatistics_b200 k3d 0.2 (sm_100a)"
 #define K3D_EPS 2.220446049250313e-16 /* 7./3-4./3-1, krige3d.py:795,853 */
 #define FULL 0xffffffffu
 // A kriging system whose elimination meets a pivot of magnitude <= K3D_SING_TOL * maxcov is
