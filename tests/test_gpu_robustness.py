@@ -15,7 +15,6 @@ import numpy as np
 import pytest
 
 import k3d_configs
-from oracle import kt3d_oracle as orc
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
